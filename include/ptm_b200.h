@@ -1,0 +1,184 @@
+/*
+ * ptm_b200.h -- C ABI of the B200 (sm_100a) PTM fit / quantise / relight library.
+ *
+ * This is the boundary a C host (the ptmlib.h drop-in in rti_b200/csrc/ptmlib_host.c,
+ * the command-line mains) or any FFI (ctypes in rti_b200/_lib.py) binds to.  Plain
+ * pointers and sizes only.  Every entry names the reference interface it stands
+ * in for; paths are relative to the reference tree (cceh/rti).
+ *
+ * Conventions
+ *   - All functions return 0 on success and a non-zero code on failure;
+ *     ptmb_last_error() then returns a message for the calling thread.  There
+ *     is no CPU fallback: without a usable CUDA device every call fails.
+ *   - `*_dev` pointers are device memory on the context's GPU.  Work is
+ *     enqueued on the context's stream and is asynchronous unless noted.
+ *   - A "stack" is the decoded image stack of the reference's encoder
+ *     (rti-builder/ptm-encoder.c:245-264): samples [light][pixel][3], pixels in
+ *     stored (already flipped) row order.  `image_stride` is the distance between two
+ *     lights' images: in BYTES for the stack entry points, in SAMPLES for ptmb_fit_channel
+ *     (which mirrors the reference's sample-indexed signature).
+ *   - Coefficient order everywhere: u^2, v^2, uv, u, v, 1 (rti-builder/ptmlib.h:37-55).
+ *   - "keys": the 12 running extrema a fit leaves behind, as order-preserving
+ *     int32 images of floats (keys[k] = key(-min_k), keys[6+k] = key(max_k)), so
+ *     that ONE integer max-reduction (atomicMax on a GPU, an int32 MAX allreduce
+ *     across GPUs) merges partial results exactly.
+ */
+#ifndef PTM_B200_H
+#define PTM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTMB_COEFFICIENTS 6
+#define PTMB_KEYS 12
+
+/* sample types of a stack */
+#define PTMB_U8  0
+#define PTMB_U16 1
+#define PTMB_U32 2
+
+/* synthetic stack content (rti_b200/csrc/ptm_synth.cu) */
+#define PTMB_SYNTH_YCBCR 0
+#define PTMB_SYNTH_RGB   1
+
+typedef struct ptmb_ctx ptmb_ctx_t;
+
+/* What ptm_scale_coefficients writes into the PTM header
+ * (rti-builder/ptmlib.h:126-127, rti-builder/ptmlib.c:858-863). */
+typedef struct {
+    float scale[PTMB_COEFFICIENTS];
+    int32_t bias[PTMB_COEFFICIENTS];
+} ptmb_scale_bias_t;
+
+const char *ptmb_last_error (void);
+int ptmb_device_count (int *count);
+
+/* One context per (process, GPU).  `stream` is a cudaStream_t owned by the caller
+ * (e.g. the framework's current stream) or NULL for a stream owned by the context. */
+int ptmb_create (int device, void *stream, ptmb_ctx_t **ctx);
+void ptmb_destroy (ptmb_ctx_t *ctx);
+int ptmb_set_stream (ptmb_ctx_t *ctx, void *stream);
+int ptmb_synchronize (ptmb_ctx_t *ctx);
+int ptmb_sm_count (const ptmb_ctx_t *ctx);
+
+/* Device memory helpers for hosts that have no allocator of their own. */
+int ptmb_malloc (ptmb_ctx_t *ctx, size_t bytes, void **dev);
+int ptmb_free (ptmb_ctx_t *ctx, void *dev);
+int ptmb_upload (ptmb_ctx_t *ctx, void *dev, const void *host, size_t bytes);
+int ptmb_download (ptmb_ctx_t *ctx, void *host, const void *dev, size_t bytes);
+int ptmb_host_register (const void *host, size_t bytes);
+int ptmb_host_unregister (const void *host);
+
+/* The 6 x n_lights pseudo-inverse from ptm_svd (rti-builder/ptmlib.c:630-689), row
+ * major, HOST pointer.  Copied to the device; valid for all later fits. */
+int ptmb_set_matrix (ptmb_ctx_t *ctx, const float *M, unsigned n_lights);
+
+/* Reset keys to the reference's initial extrema (min = FLT_MAX, max = -FLT_MAX,
+ * rti-builder/ptmlib.c:826-827). */
+int ptmb_keys_init (ptmb_ctx_t *ctx, int32_t *keys_dev);
+
+/* K1, LRGB.  Fuses, for every pixel of an interleaved 3-channel stack:
+ *   ptm_fit_poly_jsample on channel 0      rti-builder/ptmlib.c:692-725
+ *   ptm_cbcr_avg on all three channels     rti-builder/ptmlib.c:762-802
+ *   the LRGB colour + normalise loop       rti-builder/ptm-encoder.c:327-353
+ *   phase A of ptm_scale_coefficients      rti-builder/ptmlib.c:826-847 (into keys)
+ * stack_dev: samples [n_lights][pixels][3] of `sample_type`, image_stride in BYTES.
+ * coeffs_dev: float [pixels][6] (normalised), rgb_dev: uint8 [pixels][3].
+ * keys_dev is merged into (call ptmb_keys_init first). */
+int ptmb_fit_lrgb (ptmb_ctx_t *ctx, const void *stack_dev, int sample_type, size_t image_stride,
+                   size_t pixels, float *coeffs_dev, uint8_t *rgb_dev, int32_t *keys_dev);
+
+/* K1, RGB formats: three fits (rti-builder/ptm-encoder.c:272-284) in one pass.
+ * coeffs_dev: float [3][pixels][6] with `plane_stride` floats between planes.  Only plane 0
+ * feeds the extrema, as in the reference (rti-builder/ptmlib.c:831). */
+int ptmb_fit_rgb (ptmb_ctx_t *ctx, const void *stack_dev, int sample_type, size_t image_stride,
+                  size_t pixels, float *coeffs_dev, size_t plane_stride, int32_t *keys_dev);
+
+/* ptm_fit_poly_jsample / ptm_fit_poly_uint in their general form
+ * (rti-builder/ptmlib.c:692-760): one channel, arbitrary pixel stride (in samples),
+ * image_stride in SAMPLES (= height * width * pixel_stride in the reference). */
+int ptmb_fit_channel (ptmb_ctx_t *ctx, const void *samples_dev, int sample_type, size_t pixel_stride,
+                      size_t image_stride, size_t pixels, float *coeffs_dev);
+
+/* ptm_cbcr_avg alone (rti-builder/ptmlib.c:762-802): uint8 stack [n][pixels][3]. */
+int ptmb_chroma_avg (ptmb_ctx_t *ctx, const uint8_t *stack_dev, size_t image_stride,
+                     size_t pixels, unsigned n_lights, uint8_t *avg_dev);
+
+/* The LRGB colour + normalise loop alone (rti-builder/ptm-encoder.c:327-353), in place. */
+int ptmb_lrgb_colour_normalise (ptmb_ctx_t *ctx, uint8_t *ycc_to_rgb_dev, float *coeffs_dev, size_t pixels);
+
+/* Phase A of ptm_scale_coefficients alone (rti-builder/ptmlib.c:826-847). */
+int ptmb_minmax (ptmb_ctx_t *ctx, const float *coeffs_dev, size_t pixels, int32_t *keys_dev);
+
+/* K2: phases B and C of ptm_scale_coefficients (rti-builder/ptmlib.c:858-880).
+ * Derives scale / bias from keys_dev on the device (written to sb_dev if non-NULL) and
+ * quantises one coefficient plane: bytes_dev uint8 [pixels][6]. */
+int ptmb_quantise (ptmb_ctx_t *ctx, const float *coeffs_dev, size_t pixels, const int32_t *keys_dev,
+                   uint8_t *bytes_dev, ptmb_scale_bias_t *sb_dev);
+
+/* K3: the pixel loop of ptm_write_jpeg (rti-builder/ptmlib.c:553-562,587-621) for `n_dirs`
+ * light directions at once.  uv: HOST array of n_dirs (u, v) pairs.  out_dev: uint8
+ * [n_dirs][height][width][3], top row first (stored row height-1-y, :587-589).
+ * LRGB: coef_dev [pixels][6] + rgb_dev [pixels][3].  RGB: three coefficient planes. */
+int ptmb_relight_lrgb (ptmb_ctx_t *ctx, const uint8_t *coef_dev, const uint8_t *rgb_dev,
+                       size_t width, size_t height, const float *scale, const int32_t *bias,
+                       const float *uv, unsigned n_dirs, uint8_t *out_dev);
+int ptmb_relight_rgb (ptmb_ctx_t *ctx, const uint8_t *r_dev, const uint8_t *g_dev, const uint8_t *b_dev,
+                      size_t width, size_t height, const float *scale, const int32_t *bias,
+                      const float *uv, unsigned n_dirs, uint8_t *out_dev);
+
+/* Synthetic stack for pixels [pixel0, pixel0 + pixels) of every light, generated on the
+ * device (integer only; the host statement is oracle/synth.c).  lights_q14: HOST array of
+ * n_lights (x, y, z) in Q14. */
+int ptmb_synth (ptmb_ctx_t *ctx, uint32_t seed, int mode, int sample_type, uint32_t pixel0, size_t pixels,
+                unsigned n_lights, const int32_t *lights_q14, void *stack_dev, size_t image_stride);
+
+/* Whole encode with HOST buffers -- the call the ptmlib.h drop-in and the new encoder main
+ * make (it stands in for rti-builder/ptm-encoder.c:270-353,406 between "stack decoded" and
+ * "blocks ready").  The stack is streamed to the GPU in row slabs (two staging buffers, copy
+ * stream overlapped with K1; give it pinned memory for full PCIe rate), K1 runs per slab, then
+ * K2, and the blocks come back.  format_planes = 1 (LRGB: blocks[0] coefficients, blocks[1]
+ * RGB) or 3 (RGB formats: three coefficient blocks).  coeffs_host may be NULL.
+ *
+ * The two-call form exposes the one cross-GPU step: _fit leaves the slab's extrema keys on
+ * the device (copied to keys_dev when non-NULL) so a multi-GPU caller can MAX-all-reduce
+ * them before _finish (keys_dev NULL = the context's own keys).  _finish is synchronous.
+ * Scratch is kept in the context between calls; _release frees it. */
+int ptmb_encode_host_fit (ptmb_ctx_t *ctx, const void *stack_host, int sample_type, size_t width, size_t height,
+                          unsigned n_lights, const float *M, int format_planes, int32_t *keys_dev);
+int ptmb_encode_host_finish (ptmb_ctx_t *ctx, const int32_t *keys_dev, uint8_t *const *blocks_host,
+                             float *coeffs_host, ptmb_scale_bias_t *sb_host);
+int ptmb_encode_host (ptmb_ctx_t *ctx, const void *stack_host, int sample_type, size_t width, size_t height,
+                      unsigned n_lights, const float *M, int format_planes, uint8_t *const *blocks_host,
+                      float *coeffs_host, ptmb_scale_bias_t *sb_host);
+int ptmb_encode_host_release (ptmb_ctx_t *ctx);
+
+/* Host-pointer forms of the individual steps, for callers that keep the reference's own
+ * call sequence through ptmlib.h (each streams its operands through device slabs):
+ *   ptmb_fit_channel_host            ptm_fit_poly_jsample / _uint   rti-builder/ptmlib.c:692-760
+ *   ptmb_chroma_avg_host             ptm_cbcr_avg                   rti-builder/ptmlib.c:762-802
+ *   ptmb_lrgb_colour_normalise_host  the loop in the encoder main   rti-builder/ptm-encoder.c:327-353
+ *   ptmb_scale_host                  ptm_scale_coefficients         rti-builder/ptmlib.c:816-881
+ *   ptmb_relight_host                the loop of ptm_write_jpeg     rti-builder/ptmlib.c:587-621
+ * samples_host points at the first sample of the wanted channel; sample (light l, pixel p) is
+ * samples_host[(l * width * height + p) * pixel_stride], as in the reference. */
+int ptmb_fit_channel_host (ptmb_ctx_t *ctx, const void *samples_host, int sample_type, size_t pixel_stride,
+                           size_t width, size_t height, unsigned n_lights, const float *M, float *coeffs_host);
+int ptmb_chroma_avg_host (ptmb_ctx_t *ctx, const uint8_t *stack_host, size_t pixels, unsigned n_lights,
+                          uint8_t *avg_host);
+int ptmb_lrgb_colour_normalise_host (ptmb_ctx_t *ctx, uint8_t *ycc_to_rgb_host, float *coeffs_host, size_t pixels);
+int ptmb_scale_host (ptmb_ctx_t *ctx, const float *coeffs_host, size_t pixels, int planes,
+                     uint8_t *const *blocks_host, ptmb_scale_bias_t *sb_host);
+int ptmb_relight_host (ptmb_ctx_t *ctx, const uint8_t *const *blocks_host, int planes, size_t width, size_t height,
+                       const float *scale, const int32_t *bias, const float *uv, unsigned n_dirs,
+                       uint8_t *out_host);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -361,3 +361,75 @@ def ref_cbcr_avg(stack):
     info = ref_info(n, H, W)
     reflib().ptm_cbcr_avg(C.byref(info), stack.reshape(-1), out.reshape(-1))
     return out
+
+
+# ----------------------------------------------------- timed CPU baseline (bench.py)
+
+class _RefFormat(C.Structure):
+    # rti-builder/ptmlib.h:87-99
+    _fields_ = [("id", C.c_int), ("blocks", C.c_int), ("ptm_blocks", C.c_int), ("color_components", C.c_int),
+                ("jpeg_streams", C.c_int), ("name", C.c_char_p)]
+
+
+class _RefHeader(C.Structure):
+    # rti-builder/ptmlib.h:123-138 (MAX_JPEG_STREAMS expands to 3 * 6 = 18 inside the declarators)
+    _fields_ = [("format", C.POINTER(_RefFormat)), ("dimen", C.c_size_t * 2), ("scale", C.c_float * 6),
+                ("bias", C.c_int * 6), ("compression_param", C.c_int * 1), ("transforms", C.c_int * 18),
+                ("motion_vector_x", C.c_int * 18), ("motion_vector_y", C.c_int * 18), ("order", C.c_int * 18),
+                ("reference_planes", C.c_int * 18), ("compressed_size", C.c_size_t * 18),
+                ("side_info_sizes", C.c_size_t * 18)]
+
+
+def cpu_encode_lrgb_timed(stack, M, use_ref=None, threads=None):
+    """Time the reference's LRGB sequence on the host (rti-builder/ptm-encoder.c:313-353,406):
+    ptm_fit_poly_jsample -> ptm_cbcr_avg -> colour/normalise loop -> ptm_scale_coefficients.
+
+    With oracle/_ref built the three ptmlib.c functions are the reference's OWN compiled code
+    (kind "reference"); the colour loop lives in the encoder's main and is always the
+    restatement.  Otherwise everything is the port (kind "port").  Returns
+    (seconds, kind, result dict)."""
+    import time
+    if use_ref is None:
+        use_ref = os.path.exists(os.path.join(REF_DIR, "libptmref.so"))
+    if threads:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    n, H, W, _ = stack.shape
+    P = H * W
+    M = np.ascontiguousarray(M, dtype=np.float32)
+    coeffs = np.empty((P, NCOEF), np.float32)
+    rgb = np.empty((P, 3), np.uint8)
+    coef = np.empty((P, NCOEF), np.uint8)
+    lib().orc_blas_set_threads(1)
+    if use_ref:
+        R = reflib()
+        R.ptm_get_format.restype = C.POINTER(_RefFormat)
+        R.ptm_get_format.argtypes = [C.c_char_p]
+        R.ptm_scale_coefficients.argtypes = [C.POINTER(_RefHeader), _f32p, C.POINTER(C.c_void_p)]
+        R.ptm_scale_coefficients.restype = None
+        hdr = _RefHeader()
+        hdr.format = R.ptm_get_format(b"PTM_FORMAT_LRGB")
+        hdr.dimen[0], hdr.dimen[1] = W, H
+        info = ref_info(n, H, W)
+        blocks = (C.c_void_p * 2)(coef.ctypes.data, rgb.ctypes.data)
+        t0 = time.perf_counter()
+        R.ptm_fit_poly_jsample(C.byref(info), stack.ctypes.data, 3, M.reshape(-1), coeffs.reshape(-1))
+        R.ptm_cbcr_avg(C.byref(info), stack.reshape(-1), rgb.reshape(-1))
+        lib().orc_lrgb_colour_normalise(rgb.reshape(-1), coeffs.reshape(-1), P)
+        R.ptm_scale_coefficients(C.byref(hdr), coeffs.reshape(-1), blocks)
+        dt = time.perf_counter() - t0
+        sc = np.array(hdr.scale, np.float32)
+        bi = np.array(hdr.bias, np.int32)
+        kind = "reference"
+    else:
+        sc = np.zeros(NCOEF, np.float32)
+        bi = np.zeros(NCOEF, np.int32)
+        ptrs = (C.c_void_p * 1)(coef.ctypes.data)
+        t0 = time.perf_counter()
+        lib().orc_fit_u8(stack.ctypes.data, W, H, n, 3, M.reshape(-1), coeffs.reshape(-1))
+        lib().orc_chroma_avg(stack.reshape(-1), P, n, rgb.reshape(-1))
+        lib().orc_lrgb_colour_normalise(rgb.reshape(-1), coeffs.reshape(-1), P)
+        lib().orc_scale(coeffs.reshape(-1), P, 1, sc, bi, ptrs, None)
+        dt = time.perf_counter() - t0
+        kind = "port"
+    return dt, kind, dict(coeffs=coeffs.reshape(H, W, NCOEF), coef=coef.reshape(H, W, NCOEF),
+                          rgb=rgb.reshape(H, W, 3), scale=sc, bias=bi)

@@ -1,0 +1,589 @@
+// C ABI of libptm_b200.so (see include/ptm_b200.h).  Thin: argument checks,
+// context bookkeeping and launches; no arithmetic lives here.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ptm_b200.h"
+#include "ptm_device.cuh"
+#include "ptm_kernels.h"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(const char *what, const char *detail) {
+    g_error = std::string(what) + ": " + detail;
+    return 1;
+}
+
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess)                                     \
+            return fail(#call, cudaGetErrorString(e_));            \
+    } while (0)
+
+#define REQUIRE(cond, msg)                                         \
+    do {                                                           \
+        if (!(cond))                                               \
+            return fail("invalid argument", msg);                  \
+    } while (0)
+
+size_t sample_size(int sample_type) {
+    return sample_type == PTMB_U8 ? 1 : sample_type == PTMB_U16 ? 2 : sample_type == PTMB_U32 ? 4 : 0;
+}
+
+}  // namespace
+
+struct EncodeScratch {
+    void *stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    float *coeffs = nullptr;
+    size_t coeff_floats = 0;
+    uint8_t *bytes = nullptr;  // planes * pixels * 6 (+ pixels * 3 for LRGB)
+    size_t out_bytes = 0;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    size_t pixels = 0;
+    int planes = 0;
+    bool valid = false;
+};
+
+struct ptmb_ctx {
+    EncodeScratch enc;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    std::vector<float> M_host;
+    float *M_dev = nullptr;
+    unsigned n_lights = 0;
+    unsigned magic = 0;
+    int *keys_dev = nullptr;                 // scratch for the host-buffer entry points
+    ptmb_scale_bias_t *sb_dev = nullptr;
+    std::vector<float> light_host;
+    float *light_dev = nullptr;
+    size_t light_cap = 0;
+    int32_t *lq_dev = nullptr;
+    size_t lq_cap = 0;
+};
+
+extern "C" {
+
+const char *ptmb_last_error(void) { return g_error.c_str(); }
+
+// used by ptm_api_host.cu
+int ptmb_internal_fail(const char *what, const char *detail) { return fail(what, detail); }
+int ptmb_internal_device(const ptmb_ctx_t *c) { return c->device; }
+void *ptmb_internal_stream(const ptmb_ctx_t *c) { return (void *) c->stream; }
+const float *ptmb_internal_matrix(const ptmb_ctx_t *c) { return c->M_dev; }
+
+int ptmb_device_count(int *count) {
+    REQUIRE(count, "count is NULL");
+    CK(cudaGetDeviceCount(count));
+    return 0;
+}
+
+int ptmb_create(int device, void *stream, ptmb_ctx_t **out) {
+    REQUIRE(out, "ctx out pointer is NULL");
+    *out = nullptr;
+    int count = 0;
+    CK(cudaGetDeviceCount(&count));
+    if (count <= 0)
+        return fail("ptmb_create", "no CUDA device (this library has no CPU path)");
+    REQUIRE(device >= 0 && device < count, "device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail("ptmb_create", "kernels are built for sm_100a only");
+    ptmb_ctx *c = new ptmb_ctx;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        c->stream = (cudaStream_t) stream;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete c;
+            return fail("cudaStreamCreate", cudaGetErrorString(e));
+        }
+        c->own_stream = true;
+    }
+    cudaError_t e = cudaMalloc(&c->keys_dev, PTMB_KEYS * sizeof(int));
+    if (e == cudaSuccess)
+        e = cudaMalloc(&c->sb_dev, sizeof(ptmb_scale_bias_t));
+    if (e != cudaSuccess) {
+        delete c;
+        return fail("cudaMalloc", cudaGetErrorString(e));
+    }
+    *out = c;
+    return 0;
+}
+
+static void encode_scratch_release(ptmb_ctx *c);
+
+void ptmb_destroy(ptmb_ctx_t *c) {
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    encode_scratch_release(c);
+    cudaFree(c->M_dev);
+    cudaFree(c->keys_dev);
+    cudaFree(c->sb_dev);
+    cudaFree(c->light_dev);
+    cudaFree(c->lq_dev);
+    if (c->own_stream)
+        cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int ptmb_set_stream(ptmb_ctx_t *c, void *stream) {
+    REQUIRE(c, "ctx is NULL");
+    if (c->own_stream) {
+        CK(cudaSetDevice(c->device));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaStreamDestroy(c->stream));
+        c->own_stream = false;
+    }
+    if (stream) {
+        c->stream = (cudaStream_t) stream;
+    } else {
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    return 0;
+}
+
+int ptmb_synchronize(ptmb_ctx_t *c) {
+    REQUIRE(c, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ptmb_sm_count(const ptmb_ctx_t *c) { return c ? c->sm_count : 0; }
+
+int ptmb_malloc(ptmb_ctx_t *c, size_t bytes, void **dev) {
+    REQUIRE(c && dev, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMalloc(dev, bytes ? bytes : 1));
+    return 0;
+}
+
+int ptmb_free(ptmb_ctx_t *c, void *dev) {
+    REQUIRE(c, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(dev));
+    return 0;
+}
+
+int ptmb_upload(ptmb_ctx_t *c, void *dev, const void *host, size_t bytes) {
+    REQUIRE(c && (bytes == 0 || (dev && host)), "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+int ptmb_download(ptmb_ctx_t *c, void *host, const void *dev, size_t bytes) {
+    REQUIRE(c && (bytes == 0 || (dev && host)), "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ptmb_host_register(const void *host, size_t bytes) {
+    CK(cudaHostRegister(const_cast<void *>(host), bytes, cudaHostRegisterDefault));
+    return 0;
+}
+
+int ptmb_host_unregister(const void *host) {
+    CK(cudaHostUnregister(const_cast<void *>(host)));
+    return 0;
+}
+
+int ptmb_set_matrix(ptmb_ctx_t *c, const float *M, unsigned n_lights) {
+    REQUIRE(c && M, "NULL argument");
+    REQUIRE(n_lights >= 1 && n_lights <= 4096, "n_lights must be in 1..4096");
+    CK(cudaSetDevice(c->device));
+    if (n_lights != c->n_lights || !c->M_dev) {
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaFree(c->M_dev));
+        c->M_dev = nullptr;
+        CK(cudaMalloc(&c->M_dev, (size_t) n_lights * PTMB_COEFFICIENTS * sizeof(float)));
+    }
+    // the previous matrix may still be in use by queued kernels reading M_host's copy: the
+    // copy below is stream ordered, and pageable sources are staged before the call returns
+    c->M_host.assign(M, M + (size_t) n_lights * PTMB_COEFFICIENTS);
+    c->n_lights = n_lights;
+    c->magic = n_lights == 1 ? 0u : (unsigned) ((1ull << 32) / n_lights) + 1u;
+    CK(cudaMemcpyAsync(c->M_dev, c->M_host.data(), c->M_host.size() * sizeof(float), cudaMemcpyHostToDevice,
+                       c->stream));
+    return 0;
+}
+
+int ptmb_keys_init(ptmb_ctx_t *c, int32_t *keys_dev) {
+    REQUIRE(c && keys_dev, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(ptm::launch_keys_init(keys_dev, c->stream));
+    return 0;
+}
+
+static int make_fit_args(ptmb_ctx_t *c, const void *stack_dev, size_t image_stride, size_t pixels,
+                         ptm::FitArgs &a) {
+    REQUIRE(c, "ctx is NULL");
+    REQUIRE(c->M_dev, "ptmb_set_matrix has not been called");
+    REQUIRE(stack_dev || pixels == 0, "stack is NULL");
+    a.stack = (const uint8_t *) stack_dev;
+    a.image_stride = image_stride;
+    a.pixels = pixels;
+    a.n_lights = c->n_lights;
+    a.magic = c->magic;
+    a.M = c->M_dev;
+    a.coeffs = nullptr;
+    a.plane_stride = 0;
+    a.rgb = nullptr;
+    a.keys = nullptr;
+    return 0;
+}
+
+int ptmb_fit_lrgb(ptmb_ctx_t *c, const void *stack_dev, int sample_type, size_t image_stride, size_t pixels,
+                  float *coeffs_dev, uint8_t *rgb_dev, int32_t *keys_dev) {
+    ptm::FitArgs a;
+    if (make_fit_args(c, stack_dev, image_stride, pixels, a))
+        return 1;
+    REQUIRE(sample_type == PTMB_U8, "LRGB fit takes uint8 stacks (the reference's ptm_cbcr_avg is 8 bit only)");
+    REQUIRE(rgb_dev && keys_dev, "rgb / keys output is NULL");
+    REQUIRE(image_stride >= pixels * 3, "image_stride smaller than one image");
+    a.coeffs = coeffs_dev;
+    a.rgb = rgb_dev;
+    a.keys = keys_dev;
+    CK(cudaSetDevice(c->device));
+    CK(ptm::launch_fit_lrgb(a, sample_type, c->sm_count, c->stream));
+    return 0;
+}
+
+int ptmb_fit_rgb(ptmb_ctx_t *c, const void *stack_dev, int sample_type, size_t image_stride, size_t pixels,
+                 float *coeffs_dev, size_t plane_stride, int32_t *keys_dev) {
+    ptm::FitArgs a;
+    if (make_fit_args(c, stack_dev, image_stride, pixels, a))
+        return 1;
+    REQUIRE(sample_type == PTMB_U8 || sample_type == PTMB_U16, "RGB fit takes uint8 or uint16 stacks");
+    REQUIRE(coeffs_dev && keys_dev, "coeffs / keys output is NULL");
+    REQUIRE(plane_stride >= pixels * PTMB_COEFFICIENTS, "plane_stride smaller than one plane");
+    REQUIRE(image_stride >= pixels * 3 * sample_size(sample_type), "image_stride smaller than one image");
+    a.coeffs = coeffs_dev;
+    a.plane_stride = plane_stride;
+    a.keys = keys_dev;
+    CK(cudaSetDevice(c->device));
+    CK(ptm::launch_fit_rgb(a, sample_type, c->sm_count, c->stream));
+    return 0;
+}
+
+int ptmb_fit_channel(ptmb_ctx_t *c, const void *samples_dev, int sample_type, size_t pixel_stride,
+                     size_t image_stride, size_t pixels, float *coeffs_dev) {
+    REQUIRE(c && c->M_dev, "ptmb_set_matrix has not been called");
+    REQUIRE(sample_size(sample_type) != 0, "unknown sample type");
+    REQUIRE((samples_dev && coeffs_dev) || pixels == 0, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(ptm::launch_fit_channel(samples_dev, sample_type, pixel_stride, image_stride, pixels, c->n_lights,
+                               c->M_dev, coeffs_dev, c->sm_count, c->stream));
+    return 0;
+}
+
+int ptmb_chroma_avg(ptmb_ctx_t *c, const uint8_t *stack_dev, size_t image_stride, size_t pixels,
+                    unsigned n_lights, uint8_t *avg_dev) {
+    REQUIRE(c && ((stack_dev && avg_dev) || pixels == 0), "NULL argument");
+    REQUIRE(n_lights >= 1, "n_lights must be >= 1");
+    CK(cudaSetDevice(c->device));
+    CK(ptm::launch_chroma_avg(stack_dev, image_stride, pixels, n_lights, avg_dev, c->sm_count, c->stream));
+    return 0;
+}
+
+int ptmb_lrgb_colour_normalise(ptmb_ctx_t *c, uint8_t *ycc_dev, float *coeffs_dev, size_t pixels) {
+    REQUIRE(c && ((ycc_dev && coeffs_dev) || pixels == 0), "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(ptm::launch_lrgb_colour_normalise(ycc_dev, coeffs_dev, pixels, c->sm_count, c->stream));
+    return 0;
+}
+
+int ptmb_minmax(ptmb_ctx_t *c, const float *coeffs_dev, size_t pixels, int32_t *keys_dev) {
+    REQUIRE(c && keys_dev && (coeffs_dev || pixels == 0), "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(ptm::launch_minmax(coeffs_dev, pixels, keys_dev, c->sm_count, c->stream));
+    return 0;
+}
+
+int ptmb_quantise(ptmb_ctx_t *c, const float *coeffs_dev, size_t pixels, const int32_t *keys_dev,
+                  uint8_t *bytes_dev, ptmb_scale_bias_t *sb_dev) {
+    REQUIRE(c && keys_dev, "NULL argument");
+    REQUIRE((coeffs_dev && bytes_dev) || pixels == 0, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(ptm::launch_quantise(coeffs_dev, pixels, keys_dev, bytes_dev, sb_dev, c->sm_count, c->stream));
+    return 0;
+}
+
+static int relight_common(ptmb_ctx_t *c, ptm::RelightArgs &a, bool lrgb, size_t width, size_t height,
+                          const float *scale, const int32_t *bias, const float *uv, unsigned n_dirs,
+                          uint8_t *out_dev) {
+    REQUIRE(c && scale && bias, "NULL argument");
+    REQUIRE((uv && out_dev) || n_dirs == 0, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    if (n_dirs == 0 || width * height == 0)
+        return 0;
+    a.width = width;
+    a.height = height;
+    memcpy(a.scale, scale, sizeof(a.scale));
+    memcpy(a.bias, bias, sizeof(a.bias));
+    // light vector per direction (rti-builder/ptmlib.c:556-562)
+    c->light_host.resize((size_t) n_dirs * PTMB_COEFFICIENTS);
+    for (unsigned d = 0; d < n_dirs; ++d) {
+        const float u = uv[2 * d], v = uv[2 * d + 1];
+        float *l = &c->light_host[(size_t) d * PTMB_COEFFICIENTS];
+        l[0] = u * u;
+        l[1] = v * v;
+        l[2] = u * v;
+        l[3] = u;
+        l[4] = v;
+        l[5] = 1.0f;
+    }
+    if (c->light_cap < n_dirs) {
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaFree(c->light_dev));
+        c->light_dev = nullptr;
+        c->light_cap = 0;
+        CK(cudaMalloc(&c->light_dev, (size_t) n_dirs * PTMB_COEFFICIENTS * sizeof(float)));
+        c->light_cap = n_dirs;
+    }
+    CK(cudaMemcpyAsync(c->light_dev, c->light_host.data(), c->light_host.size() * sizeof(float),
+                       cudaMemcpyHostToDevice, c->stream));
+    const unsigned kBatch = 1024;  // light table lives in shared memory
+    for (unsigned d0 = 0; d0 < n_dirs; d0 += kBatch) {
+        a.n_dirs = n_dirs - d0 < kBatch ? n_dirs - d0 : kBatch;
+        a.light = c->light_dev + (size_t) d0 * PTMB_COEFFICIENTS;
+        a.out = out_dev + (size_t) d0 * width * height * 3;
+        CK(ptm::launch_relight(a, lrgb, c->sm_count, c->stream));
+    }
+    return 0;
+}
+
+int ptmb_relight_lrgb(ptmb_ctx_t *c, const uint8_t *coef_dev, const uint8_t *rgb_dev, size_t width,
+                      size_t height, const float *scale, const int32_t *bias, const float *uv, unsigned n_dirs,
+                      uint8_t *out_dev) {
+    REQUIRE((coef_dev && rgb_dev) || width * height == 0, "NULL block");
+    ptm::RelightArgs a{};
+    a.plane[0] = coef_dev;
+    a.plane[1] = rgb_dev;
+    a.plane[2] = nullptr;
+    return relight_common(c, a, true, width, height, scale, bias, uv, n_dirs, out_dev);
+}
+
+int ptmb_relight_rgb(ptmb_ctx_t *c, const uint8_t *r_dev, const uint8_t *g_dev, const uint8_t *b_dev,
+                     size_t width, size_t height, const float *scale, const int32_t *bias, const float *uv,
+                     unsigned n_dirs, uint8_t *out_dev) {
+    REQUIRE((r_dev && g_dev && b_dev) || width * height == 0, "NULL block");
+    ptm::RelightArgs a{};
+    a.plane[0] = r_dev;
+    a.plane[1] = g_dev;
+    a.plane[2] = b_dev;
+    return relight_common(c, a, false, width, height, scale, bias, uv, n_dirs, out_dev);
+}
+
+int ptmb_synth(ptmb_ctx_t *c, uint32_t seed, int mode, int sample_type, uint32_t pixel0, size_t pixels,
+               unsigned n_lights, const int32_t *lights_q14, void *stack_dev, size_t image_stride) {
+    REQUIRE(c && lights_q14 && (stack_dev || pixels == 0), "NULL argument");
+    REQUIRE(sample_type == PTMB_U8 || sample_type == PTMB_U16, "synthetic stacks are uint8 or uint16");
+    REQUIRE(mode == PTMB_SYNTH_YCBCR || mode == PTMB_SYNTH_RGB, "unknown synth mode");
+    CK(cudaSetDevice(c->device));
+    if (c->lq_cap < n_lights) {
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaFree(c->lq_dev));
+        c->lq_dev = nullptr;
+        c->lq_cap = 0;
+        CK(cudaMalloc(&c->lq_dev, (size_t) n_lights * 3 * sizeof(int32_t)));
+        c->lq_cap = n_lights;
+    }
+    CK(cudaMemcpyAsync(c->lq_dev, lights_q14, (size_t) n_lights * 3 * sizeof(int32_t), cudaMemcpyHostToDevice,
+                       c->stream));
+    CK(ptm::launch_synth(seed, mode, sample_type, pixel0, pixels, n_lights, c->lq_dev, stack_dev, image_stride,
+                         c->sm_count, c->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Whole encode from host buffers: row slabs of the stack are copied to one of two
+// device staging buffers on a copy stream while the fit kernel works on the other.
+// Scratch lives in the context and is reused while the geometry stays the same.
+// ---------------------------------------------------------------------------
+static void encode_scratch_release(ptmb_ctx *c) {
+    EncodeScratch &s = c->enc;
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(s.stage[i]);
+        s.stage[i] = nullptr;
+        if (s.copied[i])
+            cudaEventDestroy(s.copied[i]);
+        if (s.consumed[i])
+            cudaEventDestroy(s.consumed[i]);
+        s.copied[i] = s.consumed[i] = nullptr;
+    }
+    cudaFree(s.coeffs);
+    cudaFree(s.bytes);
+    s.coeffs = nullptr;
+    s.bytes = nullptr;
+    if (s.copy)
+        cudaStreamDestroy(s.copy);
+    s.copy = nullptr;
+    s.stage_bytes = s.coeff_floats = s.out_bytes = 0;
+    s.valid = false;
+}
+
+int ptmb_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, int sample_type, size_t width, size_t height,
+                         unsigned n_lights, const float *M, int format_planes, int32_t *keys_dev) {
+    REQUIRE(c && stack_host && M, "NULL argument");
+    REQUIRE(format_planes == 1 || format_planes == 3, "format_planes must be 1 (LRGB) or 3 (RGB)");
+    const size_t ss = sample_size(sample_type);
+    REQUIRE(ss == 1 || (ss == 2 && format_planes == 3), "unsupported sample type for this format");
+    const size_t pixels = width * height;
+    REQUIRE(pixels > 0, "empty image");
+    if (ptmb_set_matrix(c, M, n_lights))
+        return 1;
+    CK(cudaSetDevice(c->device));
+
+    const size_t image_bytes = pixels * 3 * ss;
+    // slab: whole rows, about 8 MiB per light and slab
+    size_t slab_rows = (8u << 20) / (width * 3 * ss);
+    if (slab_rows < 1)
+        slab_rows = 1;
+    if (slab_rows > height)
+        slab_rows = height;
+    // slab pixel counts a multiple of 4 keep every slab on the vector kernel's alignment
+    while (slab_rows < height && (slab_rows * width) % 4 != 0)
+        ++slab_rows;
+    const size_t slab_pixels = slab_rows * width;
+    const size_t slab_stride = (slab_pixels * 3 * ss + 255) & ~(size_t) 255;
+    const size_t plane_floats = pixels * PTMB_COEFFICIENTS;
+    const size_t out_bytes = pixels * PTMB_COEFFICIENTS * format_planes + (format_planes == 1 ? pixels * 3 : 0);
+
+    EncodeScratch &s = c->enc;
+    s.valid = false;
+    if (!s.copy) {
+        CK(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&s.copied[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s.consumed[i], cudaEventDisableTiming));
+        }
+    }
+    if (s.stage_bytes < slab_stride * n_lights) {
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaStreamSynchronize(s.copy));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaFree(s.stage[i]));
+            s.stage[i] = nullptr;
+        }
+        s.stage_bytes = 0;
+        for (int i = 0; i < 2; ++i)
+            CK(cudaMalloc(&s.stage[i], slab_stride * n_lights));
+        s.stage_bytes = slab_stride * n_lights;
+    }
+    if (s.coeff_floats < plane_floats * format_planes) {
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaFree(s.coeffs));
+        s.coeffs = nullptr;
+        s.coeff_floats = 0;
+        CK(cudaMalloc(&s.coeffs, plane_floats * format_planes * sizeof(float)));
+        s.coeff_floats = plane_floats * format_planes;
+    }
+    if (s.out_bytes < out_bytes) {
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaFree(s.bytes));
+        s.bytes = nullptr;
+        s.out_bytes = 0;
+        CK(cudaMalloc(&s.bytes, out_bytes));
+        s.out_bytes = out_bytes;
+    }
+    s.pixels = pixels;
+    s.planes = format_planes;
+    uint8_t *rgb_dev = s.bytes + pixels * PTMB_COEFFICIENTS * format_planes;
+
+    CK(ptm::launch_keys_init(c->keys_dev, c->stream));
+    int buf = 0;
+    for (size_t row = 0; row < height; row += slab_rows, buf ^= 1) {
+        const size_t rows = height - row < slab_rows ? height - row : slab_rows;
+        const size_t px0 = row * width, npx = rows * width;
+        CK(cudaStreamWaitEvent(s.copy, s.consumed[buf], 0));
+        for (unsigned n = 0; n < n_lights; ++n)
+            CK(cudaMemcpyAsync((uint8_t *) s.stage[buf] + n * slab_stride,
+                               (const uint8_t *) stack_host + n * image_bytes + px0 * 3 * ss, npx * 3 * ss,
+                               cudaMemcpyHostToDevice, s.copy));
+        CK(cudaEventRecord(s.copied[buf], s.copy));
+        CK(cudaStreamWaitEvent(c->stream, s.copied[buf], 0));
+        ptm::FitArgs a;
+        if (make_fit_args(c, s.stage[buf], slab_stride, npx, a))
+            return 1;
+        a.keys = c->keys_dev;
+        a.coeffs = s.coeffs + px0 * PTMB_COEFFICIENTS;
+        if (format_planes == 1) {
+            a.rgb = rgb_dev + px0 * 3;
+            CK(ptm::launch_fit_lrgb(a, sample_type, c->sm_count, c->stream));
+        } else {
+            a.plane_stride = plane_floats;
+            CK(ptm::launch_fit_rgb(a, sample_type, c->sm_count, c->stream));
+        }
+        CK(cudaEventRecord(s.consumed[buf], c->stream));
+    }
+    if (keys_dev)
+        CK(cudaMemcpyAsync(keys_dev, c->keys_dev, PTMB_KEYS * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+                           c->stream));
+    s.valid = true;
+    return 0;
+}
+
+int ptmb_encode_host_finish(ptmb_ctx_t *c, const int32_t *keys_dev, uint8_t *const *blocks_host,
+                            float *coeffs_host, ptmb_scale_bias_t *sb_host) {
+    REQUIRE(c && blocks_host && sb_host, "NULL argument");
+    EncodeScratch &s = c->enc;
+    REQUIRE(s.valid, "ptmb_encode_host_fit has not been called");
+    CK(cudaSetDevice(c->device));
+    const int32_t *keys = keys_dev ? keys_dev : c->keys_dev;
+    const size_t pixels = s.pixels, plane_floats = pixels * PTMB_COEFFICIENTS;
+    const uint8_t *rgb_dev = s.bytes + pixels * PTMB_COEFFICIENTS * s.planes;
+    for (int b = 0; b < s.planes; ++b)
+        CK(ptm::launch_quantise(s.coeffs + b * plane_floats, pixels, keys,
+                                s.bytes + (size_t) b * pixels * PTMB_COEFFICIENTS, b == 0 ? c->sb_dev : nullptr,
+                                c->sm_count, c->stream));
+    for (int b = 0; b < s.planes; ++b)
+        CK(cudaMemcpyAsync(blocks_host[b], s.bytes + (size_t) b * pixels * PTMB_COEFFICIENTS,
+                           pixels * PTMB_COEFFICIENTS, cudaMemcpyDeviceToHost, c->stream));
+    if (s.planes == 1)
+        CK(cudaMemcpyAsync(blocks_host[1], rgb_dev, pixels * 3, cudaMemcpyDeviceToHost, c->stream));
+    if (coeffs_host)
+        CK(cudaMemcpyAsync(coeffs_host, s.coeffs, plane_floats * s.planes * sizeof(float), cudaMemcpyDeviceToHost,
+                           c->stream));
+    CK(cudaMemcpyAsync(sb_host, c->sb_dev, sizeof(ptmb_scale_bias_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    s.valid = false;
+    return 0;
+}
+
+int ptmb_encode_host(ptmb_ctx_t *c, const void *stack_host, int sample_type, size_t width, size_t height,
+                     unsigned n_lights, const float *M, int format_planes, uint8_t *const *blocks_host,
+                     float *coeffs_host, ptmb_scale_bias_t *sb_host) {
+    if (ptmb_encode_host_fit(c, stack_host, sample_type, width, height, n_lights, M, format_planes, nullptr))
+        return 1;
+    return ptmb_encode_host_finish(c, nullptr, blocks_host, coeffs_host, sb_host);
+}
+
+int ptmb_encode_host_release(ptmb_ctx_t *c) {
+    REQUIRE(c, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    encode_scratch_release(c);
+    return 0;
+}
+
+}  // extern "C"

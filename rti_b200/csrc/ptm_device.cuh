@@ -1,0 +1,140 @@
+// Device-side helpers shared by the PTM kernels (sm_100a).
+//
+// Parity rules: the reference is built without FMA
+// contraction (rti-builder/Makefile:5-7), truncates float->byte after clipping
+// (rti-builder/ptmlib.h:156-158) and does its bias arithmetic in int.  This
+// translation unit is compiled with -fmad=false; the only fused multiply-adds
+// are the explicit fmaf() calls of the per-pixel dot product, whose summation
+// order the reference itself leaves to its BLAS.
+#pragma once
+
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define PTM_NCOEF 6
+
+namespace ptm {
+
+// Order-preserving int32 image of a float: a < b  <=>  key(a) < key(b).
+__host__ __device__ __forceinline__ int float_to_key(float f) {
+#ifdef __CUDA_ARCH__
+    int b = __float_as_int(f);
+#else
+    int b;
+    memcpy(&b, &f, 4);
+#endif
+    return b ^ ((b >> 31) & 0x7FFFFFFF);
+}
+
+__host__ __device__ __forceinline__ float key_to_float(int k) {
+    int b = k ^ ((k >> 31) & 0x7FFFFFFF);
+#ifdef __CUDA_ARCH__
+    return __int_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+
+// rti-builder/ptmlib.h:156-158: f > 255 -> 255, f < 0 -> 0, else truncate.
+// cvt.rzi.u32.f32 saturates (negative -> 0) and truncates; min() does the rest.
+__device__ __forceinline__ unsigned clip_u8(float f) {
+    return min(__float2uint_rz(f), 255u);
+}
+
+// Exact uint8 -> float without the conversion unit: place the byte in the
+// mantissa of 2^23 and subtract 2^23.  `sel` is a PRMT selector that moves the
+// wanted byte of `w` to byte 0 and takes bytes 1..3 from 0x4B000000.
+__device__ __forceinline__ float byte_to_float(unsigned w, unsigned sel) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f;
+}
+#define PTM_SEL_B0 0x7650u
+#define PTM_SEL_B1 0x7651u
+#define PTM_SEL_B2 0x7652u
+#define PTM_SEL_B3 0x7653u
+
+// Exact uint16 -> float the same way (selector takes two bytes).
+__device__ __forceinline__ float half_to_float_lo(unsigned w) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610u)) - 8388608.0f;
+}
+__device__ __forceinline__ float half_to_float_hi(unsigned w) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632u)) - 8388608.0f;
+}
+
+// x / d for x <= 255 * d, d < 4104, with magic = floor(2^32 / d) + 1 (0 means d == 1).
+__device__ __forceinline__ unsigned div_magic(unsigned x, unsigned magic) {
+    return magic ? __umulhi(x, magic) : x;
+}
+
+struct Extrema {
+    float mn[PTM_NCOEF];
+    float mx[PTM_NCOEF];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int k = 0; k < PTM_NCOEF; ++k) {
+            mn[k] = FLT_MAX;
+            mx[k] = -FLT_MAX;
+        }
+    }
+    // fminf/fmaxf ignore NaNs like their libm namesakes (rti-builder/ptmlib.c:90-104)
+    __device__ __forceinline__ void add(const float *c) {
+#pragma unroll
+        for (int k = 0; k < PTM_NCOEF; ++k) {
+            mn[k] = fminf(mn[k], c[k]);
+            mx[k] = fmaxf(mx[k], c[k]);
+        }
+    }
+    // warp shuffle tree, then one atomicMax per warp and coefficient on the keys
+    __device__ __forceinline__ void flush(int *keys, int *smem_keys /* [12] in shared memory */) {
+        // block-level merge in shared memory first, then 12 global atomics per block
+        if (threadIdx.x < 2 * PTM_NCOEF)
+            smem_keys[threadIdx.x] = float_to_key(-FLT_MAX);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PTM_NCOEF; ++k) {
+            float a = -mn[k], b = mx[k];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                a = fmaxf(a, __shfl_xor_sync(0xFFFFFFFFu, a, off));
+                b = fmaxf(b, __shfl_xor_sync(0xFFFFFFFFu, b, off));
+            }
+            if ((threadIdx.x & 31) == 0) {
+                atomicMax(&smem_keys[k], float_to_key(a));
+                atomicMax(&smem_keys[PTM_NCOEF + k], float_to_key(b));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * PTM_NCOEF)
+            atomicMax(&keys[threadIdx.x], smem_keys[threadIdx.x]);
+    }
+};
+
+// The LRGB colour + normalise step for one pixel (rti-builder/ptm-encoder.c:331-348).
+// (ya, cba, cra) are the truncated integer averages of rti-builder/ptmlib.c:794-796.
+__device__ __forceinline__ void lrgb_finish(unsigned ya, unsigned cba, unsigned cra, float *c,
+                                            unsigned &r, unsigned &g, unsigned &b) {
+    const float y = (float) ya;
+    const float cb = (float) ((int) cba - 128);
+    const float cr = (float) ((int) cra - 128);
+    r = clip_u8(__fadd_rn(y, __fmul_rn(1.40200f, cr)));
+    g = clip_u8(__fsub_rn(__fsub_rn(y, __fmul_rn(0.34414f, cb)), __fmul_rn(0.71414f, cr)));
+    b = clip_u8(__fadd_rn(y, __fmul_rn(1.77200f, cb)));
+    const float norm = __fdiv_rn(256.0f, y);
+#pragma unroll
+    for (int k = 0; k < PTM_NCOEF; ++k)
+        c[k] = __fmul_rn(c[k], norm);
+}
+
+// scale / bias / inverse scale from the extrema (rti-builder/ptmlib.c:858-863).
+__device__ __forceinline__ void scale_bias_from_keys(const int *keys, int k, float &scale, int &bias, float &inv) {
+    const float mn = -key_to_float(keys[k]);
+    const float mx = key_to_float(keys[PTM_NCOEF + k]);
+    const float range = __fsub_rn(mx, mn);
+    scale = __fdiv_rn(range, 256.0f);
+    bias = (int) __fmul_rn(__fdiv_rn(-256.0f, range), mn);
+    inv = __fdiv_rn(1.0f, scale);
+}
+
+}  // namespace ptm

@@ -1,0 +1,123 @@
+// K2 -- scale / bias derivation and uint8 quantisation
+// (phases B and C of ptm_scale_coefficients, rti-builder/ptmlib.c:858-880).
+//
+// The coefficient plane is a flat float array whose element e belongs to
+// coefficient e % 6.  Each thread handles float4 q (elements 4q..4q+3), so its
+// coefficient pattern depends only on q % 3; the grid stride is a multiple of 3
+// float4s, which makes that pattern a per-thread constant held in registers.
+// Loads are 16 B per lane, stores 4 B per lane, both fully coalesced.
+#include "ptm_device.cuh"
+#include "ptm_kernels.h"
+
+namespace ptm {
+
+constexpr int kQuantThreads = 384;  // multiple of 3 and of 32
+constexpr int kQuantUnroll = 4;
+
+__global__ void __launch_bounds__(kQuantThreads)
+quantise_kernel(const float *__restrict__ coeffs, size_t n_float4, size_t tail_first, size_t n_floats,
+                const int *__restrict__ keys, uint8_t *__restrict__ bytes, void *sb_out) {
+    __shared__ float inv_s[PTM_NCOEF];
+    __shared__ float bias_s[PTM_NCOEF];
+    if (threadIdx.x < PTM_NCOEF) {
+        float scale, inv;
+        int bias;
+        scale_bias_from_keys(keys, threadIdx.x, scale, bias, inv);
+        inv_s[threadIdx.x] = inv;
+        bias_s[threadIdx.x] = (float) bias;
+        if (blockIdx.x == 0 && sb_out) {
+            reinterpret_cast<float *>(sb_out)[threadIdx.x] = scale;
+            reinterpret_cast<int *>(sb_out)[PTM_NCOEF + threadIdx.x] = bias;
+        }
+    }
+    __syncthreads();
+
+    const int k0 = (4 * (threadIdx.x % 3)) % PTM_NCOEF;  // coefficient of the float4's first lane
+    float inv[4], bias[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        inv[j] = inv_s[(k0 + j) % PTM_NCOEF];
+        bias[j] = bias_s[(k0 + j) % PTM_NCOEF];
+    }
+
+    const float4 *src = reinterpret_cast<const float4 *>(coeffs);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(bytes);
+    const size_t step = (size_t) gridDim.x * kQuantThreads;  // multiple of 3
+    size_t q = (size_t) blockIdx.x * kQuantThreads + threadIdx.x;
+
+    for (; q + (kQuantUnroll - 1) * step < n_float4; q += kQuantUnroll * step) {
+        float4 v[kQuantUnroll];
+#pragma unroll
+        for (int u = 0; u < kQuantUnroll; ++u)
+            v[u] = __ldcs(src + q + u * step);
+#pragma unroll
+        for (int u = 0; u < kQuantUnroll; ++u) {
+            const unsigned b0 = clip_u8(__fadd_rn(__fmul_rn(v[u].x, inv[0]), bias[0]));
+            const unsigned b1 = clip_u8(__fadd_rn(__fmul_rn(v[u].y, inv[1]), bias[1]));
+            const unsigned b2 = clip_u8(__fadd_rn(__fmul_rn(v[u].z, inv[2]), bias[2]));
+            const unsigned b3 = clip_u8(__fadd_rn(__fmul_rn(v[u].w, inv[3]), bias[3]));
+            __stcs(dst + q + u * step, b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+        }
+    }
+    for (; q < n_float4; q += step) {
+        const float4 v = __ldcs(src + q);
+        const unsigned b0 = clip_u8(__fadd_rn(__fmul_rn(v.x, inv[0]), bias[0]));
+        const unsigned b1 = clip_u8(__fadd_rn(__fmul_rn(v.y, inv[1]), bias[1]));
+        const unsigned b2 = clip_u8(__fadd_rn(__fmul_rn(v.z, inv[2]), bias[2]));
+        const unsigned b3 = clip_u8(__fadd_rn(__fmul_rn(v.w, inv[3]), bias[3]));
+        __stcs(dst + q, b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+    }
+    // scalar tail (fewer than 4 floats) and unaligned fallbacks
+    if (blockIdx.x == 0) {
+        for (size_t e = tail_first + threadIdx.x; e < n_floats; e += kQuantThreads) {
+            const int k = (int) (e % PTM_NCOEF);
+            bytes[e] = (uint8_t) clip_u8(__fadd_rn(__fmul_rn(coeffs[e], inv_s[k]), bias_s[k]));
+        }
+    }
+}
+
+// Everything through the scalar path: used when pointers are not 16 / 4 byte aligned.
+__global__ void __launch_bounds__(kQuantThreads)
+quantise_scalar_kernel(const float *__restrict__ coeffs, size_t n_floats, const int *__restrict__ keys,
+                       uint8_t *__restrict__ bytes, void *sb_out) {
+    __shared__ float inv_s[PTM_NCOEF];
+    __shared__ float bias_s[PTM_NCOEF];
+    if (threadIdx.x < PTM_NCOEF) {
+        float scale, inv;
+        int bias;
+        scale_bias_from_keys(keys, threadIdx.x, scale, bias, inv);
+        inv_s[threadIdx.x] = inv;
+        bias_s[threadIdx.x] = (float) bias;
+        if (blockIdx.x == 0 && sb_out) {
+            reinterpret_cast<float *>(sb_out)[threadIdx.x] = scale;
+            reinterpret_cast<int *>(sb_out)[PTM_NCOEF + threadIdx.x] = bias;
+        }
+    }
+    __syncthreads();
+    for (size_t e = (size_t) blockIdx.x * kQuantThreads + threadIdx.x; e < n_floats;
+         e += (size_t) gridDim.x * kQuantThreads) {
+        const int k = (int) (e % PTM_NCOEF);
+        bytes[e] = (uint8_t) clip_u8(__fadd_rn(__fmul_rn(coeffs[e], inv_s[k]), bias_s[k]));
+    }
+}
+
+cudaError_t launch_quantise(const float *coeffs, size_t pixels, const int *keys, uint8_t *bytes, void *sb,
+                            int sm_count, cudaStream_t st) {
+    const size_t n_floats = pixels * PTM_NCOEF;
+    const bool aligned = ((uintptr_t) coeffs % 16 == 0) && ((uintptr_t) bytes % 4 == 0);
+    if (!aligned) {
+        size_t want = (n_floats + kQuantThreads - 1) / kQuantThreads;
+        size_t cap = (size_t) sm_count * 16;
+        unsigned grid = (unsigned) (want < 1 ? 1 : (want < cap ? want : cap));
+        quantise_scalar_kernel<<<grid, kQuantThreads, 0, st>>>(coeffs, n_floats, keys, bytes, sb);
+        return cudaGetLastError();
+    }
+    const size_t n_float4 = n_floats / 4;
+    size_t want = (n_float4 + (size_t) kQuantThreads * kQuantUnroll - 1) / ((size_t) kQuantThreads * kQuantUnroll);
+    size_t cap = (size_t) sm_count * 5;
+    unsigned grid = (unsigned) (want < 1 ? 1 : (want < cap ? want : cap));
+    quantise_kernel<<<grid, kQuantThreads, 0, st>>>(coeffs, n_float4, n_float4 * 4, n_floats, keys, bytes, sb);
+    return cudaGetLastError();
+}
+
+}  // namespace ptm

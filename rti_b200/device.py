@@ -1,0 +1,190 @@
+"""Device-resident PTM pipeline: a thin object layer over the C ABI.
+
+Pointers are plain integers (``tensor.data_ptr()`` of a CUDA tensor, or memory
+from ``Context.malloc``).  PyTorch is used by callers for device memory, streams
+and the cross-GPU exchange; it is plumbing, not the product.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import NCOEF, NKEYS, U8, U16, U32, PtmError, ScaleBias  # noqa: F401
+
+
+def _ptr(x):
+    """int / None / numpy array / torch tensor -> address."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    raise TypeError("cannot take the address of %r" % type(x))
+
+
+class Context:
+    """One per (process, GPU).  ``stream`` is a raw cudaStream_t handle (int),
+    e.g. ``torch.cuda.current_stream().cuda_stream``, or None for an own stream."""
+
+    def __init__(self, device=0, stream=None):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._lib.ptmb_create(int(device), stream, C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.n_lights = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ptmb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------ plumbing
+    @property
+    def sm_count(self):
+        return self._lib.ptmb_sm_count(self._h)
+
+    def set_stream(self, stream):
+        _lib.check(self._lib.ptmb_set_stream(self._h, stream))
+
+    def synchronize(self):
+        _lib.check(self._lib.ptmb_synchronize(self._h))
+
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        _lib.check(self._lib.ptmb_malloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def free(self, ptr):
+        _lib.check(self._lib.ptmb_free(self._h, ptr))
+
+    def upload(self, dev, host):
+        host = np.ascontiguousarray(host)
+        _lib.check(self._lib.ptmb_upload(self._h, _ptr(dev), host.ctypes.data, host.nbytes))
+        self.synchronize()
+
+    def download(self, dev, shape, dtype):
+        out = np.empty(shape, dtype=dtype)
+        _lib.check(self._lib.ptmb_download(self._h, out.ctypes.data, _ptr(dev), out.nbytes))
+        return out
+
+    # ------------------------------------------------------------- kernels
+    def set_matrix(self, M):
+        M = np.ascontiguousarray(M, dtype=np.float32)
+        assert M.ndim == 2 and M.shape[0] == NCOEF, "M must be 6 x n_lights"
+        _lib.check(self._lib.ptmb_set_matrix(self._h, M.ctypes.data, M.shape[1]))
+        self.n_lights = M.shape[1]
+
+    def keys_init(self, keys):
+        _lib.check(self._lib.ptmb_keys_init(self._h, _ptr(keys)))
+
+    def fit_lrgb(self, stack, image_stride, pixels, coeffs, rgb, keys, sample_type=U8):
+        _lib.check(self._lib.ptmb_fit_lrgb(self._h, _ptr(stack), sample_type, image_stride, pixels,
+                                           _ptr(coeffs), _ptr(rgb), _ptr(keys)))
+
+    def fit_rgb(self, stack, image_stride, pixels, coeffs, plane_stride, keys, sample_type=U8):
+        _lib.check(self._lib.ptmb_fit_rgb(self._h, _ptr(stack), sample_type, image_stride, pixels,
+                                          _ptr(coeffs), plane_stride, _ptr(keys)))
+
+    def fit_channel(self, samples, sample_type, pixel_stride, image_stride, pixels, coeffs):
+        _lib.check(self._lib.ptmb_fit_channel(self._h, _ptr(samples), sample_type, pixel_stride, image_stride,
+                                              pixels, _ptr(coeffs)))
+
+    def chroma_avg(self, stack, image_stride, pixels, n_lights, avg):
+        _lib.check(self._lib.ptmb_chroma_avg(self._h, _ptr(stack), image_stride, pixels, n_lights, _ptr(avg)))
+
+    def lrgb_colour_normalise(self, ycc, coeffs, pixels):
+        _lib.check(self._lib.ptmb_lrgb_colour_normalise(self._h, _ptr(ycc), _ptr(coeffs), pixels))
+
+    def minmax(self, coeffs, pixels, keys):
+        _lib.check(self._lib.ptmb_minmax(self._h, _ptr(coeffs), pixels, _ptr(keys)))
+
+    def quantise(self, coeffs, pixels, keys, out_bytes, scale_bias=None):
+        _lib.check(self._lib.ptmb_quantise(self._h, _ptr(coeffs), pixels, _ptr(keys), _ptr(out_bytes),
+                                           _ptr(scale_bias)))
+
+    def relight_lrgb(self, coef, rgb, width, height, scale, bias, uv, out):
+        scale = np.ascontiguousarray(scale, dtype=np.float32)
+        bias = np.ascontiguousarray(bias, dtype=np.int32)
+        uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+        _lib.check(self._lib.ptmb_relight_lrgb(self._h, _ptr(coef), _ptr(rgb), width, height, scale.ctypes.data,
+                                               bias.ctypes.data, uv.ctypes.data, uv.shape[0], _ptr(out)))
+
+    def relight_rgb(self, r, g, b, width, height, scale, bias, uv, out):
+        scale = np.ascontiguousarray(scale, dtype=np.float32)
+        bias = np.ascontiguousarray(bias, dtype=np.int32)
+        uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+        _lib.check(self._lib.ptmb_relight_rgb(self._h, _ptr(r), _ptr(g), _ptr(b), width, height,
+                                              scale.ctypes.data, bias.ctypes.data, uv.ctypes.data, uv.shape[0],
+                                              _ptr(out)))
+
+    def synth(self, seed, mode, sample_type, pixel0, pixels, lights_q14, stack, image_stride):
+        lq = np.ascontiguousarray(lights_q14, dtype=np.int32).reshape(-1, 3)
+        _lib.check(self._lib.ptmb_synth(self._h, seed, mode, sample_type, pixel0, pixels, lq.shape[0],
+                                        lq.ctypes.data, _ptr(stack), image_stride))
+
+    def encode_host_fit(self, stack, shape, sample_type, M, planes=1, keys_out=None):
+        """First half of the host-buffer encode: stream the HOST stack (address or numpy array,
+        [n][H][W][3]) through K1.  Leaves the extrema keys on the device (copied to
+        ``keys_out`` if given) so that ranks can exchange them before encode_host_finish."""
+        n, H, W = shape
+        M = np.ascontiguousarray(M, dtype=np.float32)
+        self._enc_geom = (H, W, planes)
+        _lib.check(self._lib.ptmb_encode_host_fit(self._h, _ptr(stack), sample_type, W, H, n, M.ctypes.data,
+                                                  planes, _ptr(keys_out)))
+
+    def encode_host_finish(self, keys=None, out=None, want_coeffs=False):
+        """Second half: K2 with ``keys`` (None = the context's own) and D2H of the blocks into
+        ``out`` (host arrays / pinned tensors; allocated if None).  Synchronous."""
+        H, W, planes = self._enc_geom
+        P = H * W
+        if out is not None:
+            blocks = out
+        elif planes == 1:
+            blocks = [np.empty((H, W, NCOEF), np.uint8), np.empty((H, W, 3), np.uint8)]
+        else:
+            blocks = [np.empty((H, W, NCOEF), np.uint8) for _ in range(3)]
+        coeffs = np.empty((planes, P, NCOEF), np.float32) if want_coeffs else None
+        sb = ScaleBias()
+        ptrs = (C.c_void_p * len(blocks))(*[_ptr(b) for b in blocks])
+        _lib.check(self._lib.ptmb_encode_host_finish(self._h, _ptr(keys), ptrs,
+                                                     None if coeffs is None else coeffs.ctypes.data,
+                                                     C.addressof(sb)))
+        return dict(blocks=blocks, scale=np.array(sb.scale, dtype=np.float32),
+                    bias=np.array(sb.bias, dtype=np.int32), coeffs=coeffs)
+
+    def encode_host(self, stack, M, planes=1, want_coeffs=False, out=None):
+        """Whole encode from a HOST numpy stack [n][H][W][3] (uint8, or uint16 for planes=3).
+        Returns dict(blocks, scale, bias, coeffs)."""
+        assert stack.ndim == 4 and stack.shape[3] == 3 and stack.flags.c_contiguous
+        n, H, W, _ = stack.shape
+        st = {np.dtype(np.uint8): U8, np.dtype(np.uint16): U16}[stack.dtype]
+        self.encode_host_fit(stack, (n, H, W), st, M, planes)
+        return self.encode_host_finish(None, out, want_coeffs)
+
+    def encode_host_release(self):
+        _lib.check(self._lib.ptmb_encode_host_release(self._h))
+
+
+def light_q14(lights):
+    """Q14 fixed-point light directions for the synthetic generator (round half away)."""
+    l = np.asarray(lights, dtype=np.float32).reshape(-1, 3) * np.float32(16384.0)
+    return np.where(l >= 0, l + np.float32(0.5), l - np.float32(0.5)).astype(np.int32)
+
+
+def key_to_float(keys):
+    """Decode order-preserving int32 keys (numpy) back to floats."""
+    k = np.asarray(keys, dtype=np.int32)
+    b = k ^ ((k >> 31) & 0x7FFFFFFF)
+    return b.view(np.float32)

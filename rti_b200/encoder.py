@@ -1,0 +1,121 @@
+"""Device-resident PTM encode / relight pipelines (one process per GPU).
+
+The arithmetic is in the CUDA library; this module only owns buffers (torch
+tensors), enqueues K1 -> [exchange] -> K2 on torch's current stream and, when a
+process group is given, merges the twelve extrema across GPUs with ONE int32
+MAX all-reduce over NCCL (the only cross-GPU step of the whole path: every
+other step is per pixel).  The keys are order-preserving integer images of the
+floats, so the reduction is exact and the sharded result is bit-identical to
+the single-GPU one.
+
+Call order mirrors the reference encoder (rti-builder/ptm-encoder.c:307-353,406):
+fit -> chroma average -> colour/normalise (all inside K1) -> scale (K2).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .device import NCOEF, NKEYS, U8, U16, Context, key_to_float
+
+
+def slab_rows(height, world_size, rank):
+    """Contiguous row slab of rank `rank`: [floor(r*H/G), floor((r+1)*H/G))."""
+    r0 = (rank * height) // world_size
+    r1 = ((rank + 1) * height) // world_size
+    return r0, r1
+
+
+def allreduce_keys(keys, group=None):
+    """Merge extrema keys across ranks (exact: integer MAX)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=group)
+    return keys
+
+
+class PtmEncoder:
+    """LRGB (planes=1) or RGB-format (planes=3) encoder for one row slab held in HBM.
+
+    stack: CUDA uint8 tensor [n_lights, rows, width, 3] (stored row order)."""
+
+    def __init__(self, width, rows, M, planes=1, device=None, group=None, keep_coeffs=True):
+        assert torch.cuda.is_available(), "rti_b200 needs a CUDA device (no CPU fallback)"
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.width, self.rows, self.planes = int(width), int(rows), int(planes)
+        self.pixels = self.width * self.rows
+        self.group = group
+        self.ctx = Context(self.device.index, stream=torch.cuda.current_stream(self.device).cuda_stream)
+        self.ctx.set_matrix(M)
+        self.n_lights = self.ctx.n_lights
+        P = self.pixels
+        dev = self.device
+        self.coeffs = torch.empty((self.planes, P, NCOEF), dtype=torch.float32, device=dev)
+        self.coef_bytes = torch.empty((self.planes, P, NCOEF), dtype=torch.uint8, device=dev)
+        self.rgb = torch.empty((P, 3), dtype=torch.uint8, device=dev) if self.planes == 1 else None
+        self.keys = torch.empty(NKEYS, dtype=torch.int32, device=dev)
+        self.sb = torch.empty(NKEYS, dtype=torch.int32, device=dev)  # 6 floats + 6 ints, raw
+        self.launches_per_encode = 2 + self.planes
+
+    def _use_current_stream(self):
+        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def fit(self, stack):
+        """K1 on the slab; leaves float coefficients (+ RGB) and local extrema keys."""
+        assert stack.is_cuda and stack.is_contiguous()
+        n = stack.shape[0]
+        assert n == self.n_lights and stack.numel() == n * self.pixels * 3
+        st = {torch.uint8: U8, torch.uint16: U16}[stack.dtype]
+        image_stride = self.pixels * 3 * stack.element_size()
+        self.ctx.keys_init(self.keys)
+        if self.planes == 1:
+            self.ctx.fit_lrgb(stack, image_stride, self.pixels, self.coeffs, self.rgb, self.keys, st)
+        else:
+            self.ctx.fit_rgb(stack, image_stride, self.pixels, self.coeffs, self.pixels * NCOEF, self.keys, st)
+
+    def exchange(self):
+        allreduce_keys(self.keys, self.group)
+
+    def quantise(self):
+        """K2: scale/bias from the (global) keys, then bytes for every plane."""
+        for b in range(self.planes):
+            self.ctx.quantise(self.coeffs[b], self.pixels, self.keys, self.coef_bytes[b],
+                              self.sb if b == 0 else None)
+
+    def encode(self, stack):
+        self.fit(stack)
+        self.exchange()
+        self.quantise()
+
+    # ---- results (synchronising)
+    def scale_bias(self):
+        raw = self.sb.cpu().numpy()
+        return raw[:NCOEF].view(np.float32).copy(), raw[NCOEF:].copy()
+
+    def minmax(self):
+        f = key_to_float(self.keys.cpu().numpy())
+        return -f[:NCOEF], f[NCOEF:]
+
+
+class PtmRelighter:
+    """Batched relighting of a PTM held in HBM (K3)."""
+
+    def __init__(self, width, height, device=None):
+        assert torch.cuda.is_available(), "rti_b200 needs a CUDA device (no CPU fallback)"
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.width, self.height = int(width), int(height)
+        self.ctx = Context(self.device.index, stream=torch.cuda.current_stream(self.device).cuda_stream)
+
+    def relight_lrgb(self, coef, rgb, scale, bias, uv, out=None):
+        uv = np.asarray(uv, dtype=np.float32).reshape(-1, 2)
+        if out is None:
+            out = torch.empty((uv.shape[0], self.height, self.width, 3), dtype=torch.uint8, device=self.device)
+        self.ctx.relight_lrgb(coef, rgb, self.width, self.height, scale, bias, uv, out)
+        return out
+
+    def relight_rgb(self, r, g, b, scale, bias, uv, out=None):
+        uv = np.asarray(uv, dtype=np.float32).reshape(-1, 2)
+        if out is None:
+            out = torch.empty((uv.shape[0], self.height, self.width, 3), dtype=torch.uint8, device=self.device)
+        self.ctx.relight_rgb(r, g, b, self.width, self.height, scale, bias, uv, out)
+        return out

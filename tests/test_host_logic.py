@@ -1,0 +1,65 @@
+"""CPU tests of the host-side logic around the kernels."""
+import numpy as np
+
+from rti_b200 import lights
+from rti_b200.device import key_to_float, light_q14
+from rti_b200.encoder import slab_rows
+
+
+def float_to_key(f):
+    b = np.asarray(f, np.float32).view(np.int32)
+    return b ^ ((b >> 31) & 0x7FFFFFFF)
+
+
+def test_keys_preserve_float_order():
+    rng = np.random.default_rng(0)
+    f = np.concatenate([rng.normal(scale=1e3, size=1000), [0.0, -0.0, 1e-38, -1e-38, 3.4e38, -3.4e38,
+                                                              np.inf, -np.inf]]).astype(np.float32)
+    k = float_to_key(f)
+    # total order of the keys = float order, with -0.0 sorted just below +0.0
+    order_f = np.lexsort((~np.signbit(f), f))
+    assert np.all(np.diff(k[order_f].astype(np.int64)) >= 0)
+    np.testing.assert_array_equal(key_to_float(k).view(np.int32), f.view(np.int32))
+    # max over keys == key of max, so an integer MAX reduction is an exact float max
+    assert key_to_float(np.array([k.max()]))[0] == f.max()
+    assert -key_to_float(np.array([float_to_key(-f).max()]))[0] == f.min()
+
+
+def test_magic_division_is_exact():
+    # K1 divides byte sums by the light count with one multiply-high (ptm_device.cuh div_magic)
+    for d in list(range(2, 258)) + [300, 1000, 4096]:
+        magic = (1 << 32) // d + 1
+        x = np.arange(0, 255 * d + 1, dtype=np.uint64)
+        np.testing.assert_array_equal((x * magic) >> 32, x // d)
+
+
+def test_slab_partition_covers_rows():
+    for H in (1, 7, 4000, 4001, 5792):
+        for G in (1, 2, 3, 4, 8):
+            parts = [slab_rows(H, G, r) for r in range(G)]
+            assert parts[0][0] == 0 and parts[-1][1] == H
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+
+
+def test_light_sets():
+    d = lights.dome1_lights()
+    assert d.shape == (60, 3) and d.dtype == np.float32
+    file_rows = lights.read_skeleton_lp(lights.dome1_lp_path())
+    np.testing.assert_array_equal(d, file_rows)
+    np.testing.assert_allclose((d.astype(np.float64) ** 2).sum(1), 1.0, atol=2e-6)
+    assert lights.dome100_lights().shape == (100, 3)
+
+
+def test_lp_grammar(tmp_path):
+    # rti-builder/ptm-encoder.c:152-157: count line skipped, w optional
+    p = tmp_path / "s.lp"
+    p.write_text("3\na.jpg 0.1 0.2 0.97\nb.jpg -0.5 0.25\n\njunk\nc.jpg 0 0 1\n")
+    names, L = lights.read_lp(str(p))
+    assert names == ["a.jpg", "b.jpg", "c.jpg"]
+    np.testing.assert_allclose(L, [[0.1, 0.2, 0.97], [-0.5, 0.25, 0.0], [0, 0, 1]], rtol=1e-6)
+
+
+def test_light_q14_matches_oracle():
+    from oracle import oracle as O
+    d = lights.dome1_lights()
+    np.testing.assert_array_equal(light_q14(d), O.light_q14(d))
