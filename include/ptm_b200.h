@@ -57,8 +57,8 @@ typedef struct {
 const char *ptmb_last_error (void);
 int ptmb_device_count (int *count);
 
-/* One context per (process, GPU).  `stream` is a cudaStream_t owned by the caller
- * (e.g. the framework's current stream) or NULL for a stream owned by the context. */
+/* One context per (process, GPU).  `stream` is a cudaStream_t owned by the caller (e.g. the
+ * framework's current stream); NULL is the CUDA default stream. */
 int ptmb_create (int device, void *stream, ptmb_ctx_t **ctx);
 void ptmb_destroy (ptmb_ctx_t *ctx);
 int ptmb_set_stream (ptmb_ctx_t *ctx, void *stream);

@@ -55,7 +55,6 @@ struct ptmb_ctx {
     EncodeScratch enc;
     int device = 0;
     cudaStream_t stream = nullptr;
-    bool own_stream = false;
     int sm_count = 0;
     std::vector<float> M_host;
     float *M_dev = nullptr;
@@ -102,16 +101,7 @@ int ptmb_create(int device, void *stream, ptmb_ctx_t **out) {
     ptmb_ctx *c = new ptmb_ctx;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    if (stream) {
-        c->stream = (cudaStream_t) stream;
-    } else {
-        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-        if (e != cudaSuccess) {
-            delete c;
-            return fail("cudaStreamCreate", cudaGetErrorString(e));
-        }
-        c->own_stream = true;
-    }
+    c->stream = (cudaStream_t) stream;  // NULL = the CUDA default stream
     cudaError_t e = cudaMalloc(&c->keys_dev, PTMB_KEYS * sizeof(int));
     if (e == cudaSuccess)
         e = cudaMalloc(&c->sb_dev, sizeof(ptmb_scale_bias_t));
@@ -136,25 +126,12 @@ void ptmb_destroy(ptmb_ctx_t *c) {
     cudaFree(c->sb_dev);
     cudaFree(c->light_dev);
     cudaFree(c->lq_dev);
-    if (c->own_stream)
-        cudaStreamDestroy(c->stream);
     delete c;
 }
 
 int ptmb_set_stream(ptmb_ctx_t *c, void *stream) {
     REQUIRE(c, "ctx is NULL");
-    if (c->own_stream) {
-        CK(cudaSetDevice(c->device));
-        CK(cudaStreamSynchronize(c->stream));
-        CK(cudaStreamDestroy(c->stream));
-        c->own_stream = false;
-    }
-    if (stream) {
-        c->stream = (cudaStream_t) stream;
-    } else {
-        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        c->own_stream = true;
-    }
+    c->stream = (cudaStream_t) stream;
     return 0;
 }
 

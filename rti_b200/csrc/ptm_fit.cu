@@ -22,7 +22,7 @@ namespace ptm {
 // added into two accumulators per word (sums <= 255 * n < 65536 for n <= 257).
 // ---------------------------------------------------------------------------
 template <bool kWriteCoeffs>
-__global__ void __launch_bounds__(kFitThreads)
+__global__ void __launch_bounds__(kFitThreads, 3)
 fit_lrgb_u8_kernel(FitArgs a) {
     extern __shared__ float4 m_s[];  // [n][2]: (m0 m1 m2 m3) (m4 m5 0 0)
     __shared__ int keys_s[2 * PTM_NCOEF];
@@ -345,13 +345,19 @@ cudaError_t launch_keys_init(int *keys, cudaStream_t st) {
 cudaError_t launch_fit_lrgb(const FitArgs &a, int sample_type, int sm_count, cudaStream_t st) {
     if (a.pixels == 0)
         return cudaSuccess;
-    const bool vec_ok = sample_type == 0 && a.n_lights <= 257 && ((uintptr_t) a.stack % 4 == 0) &&
-                        (a.image_stride % 4 == 0) && ((uintptr_t) a.rgb % 4 == 0) &&
-                        (a.coeffs == nullptr || (uintptr_t) a.coeffs % 16 == 0);
+    if (sample_type != 0)
+        return cudaErrorInvalidValue;
+    // 1) whole 1024-pixel tiles through the streaming (bulk copy) kernel when the layout allows it
     size_t done = 0;
-    if (vec_ok && a.pixels >= 4) {
+    cudaError_t e = launch_fit_lrgb_tma(a, sm_count, st, &done);
+    if (e != cudaSuccess)
+        return e;
+    // 2) otherwise 4-pixel groups through the register kernel (word-aligned layouts)
+    const bool vec_ok = a.n_lights <= 257 && ((uintptr_t) a.stack % 4 == 0) && (a.image_stride % 4 == 0) &&
+                        ((uintptr_t) a.rgb % 4 == 0) && (a.coeffs == nullptr || (uintptr_t) a.coeffs % 16 == 0);
+    if (done == 0 && vec_ok && a.pixels >= 4) {
         const size_t groups = a.pixels / 4;
-        const unsigned grid = grid_for(groups, kFitThreads, sm_count, 4);
+        const unsigned grid = grid_for(groups, kFitThreads, sm_count, 3);
         const size_t smem = (size_t) a.n_lights * 2 * sizeof(float4);
         if (a.coeffs)
             fit_lrgb_u8_kernel<true><<<grid, kFitThreads, smem, st>>>(a);
@@ -359,14 +365,10 @@ cudaError_t launch_fit_lrgb(const FitArgs &a, int sample_type, int sm_count, cud
             fit_lrgb_u8_kernel<false><<<grid, kFitThreads, smem, st>>>(a);
         done = groups * 4;
     }
+    // 3) whatever is left (tile / group remainders, unaligned stacks, > 257 lights): one pixel per thread
     if (done < a.pixels) {
         const unsigned grid = grid_for(a.pixels - done, kFitThreads, sm_count, 8);
-        if (sample_type == 0)
-            fit_lrgb_generic_kernel<uint8_t><<<grid, kFitThreads, 0, st>>>(a, done);
-        else if (sample_type == 1)
-            fit_lrgb_generic_kernel<uint16_t><<<grid, kFitThreads, 0, st>>>(a, done);
-        else
-            return cudaErrorInvalidValue;
+        fit_lrgb_generic_kernel<uint8_t><<<grid, kFitThreads, 0, st>>>(a, done);
     }
     return cudaGetLastError();
 }

@@ -29,7 +29,7 @@ def _ptr(x):
 
 class Context:
     """One per (process, GPU).  ``stream`` is a raw cudaStream_t handle (int),
-    e.g. ``torch.cuda.current_stream().cuda_stream``, or None for an own stream."""
+    e.g. ``torch.cuda.current_stream().cuda_stream``; None / 0 is the CUDA default stream."""
 
     def __init__(self, device=0, stream=None):
         self._lib = _lib.load()
