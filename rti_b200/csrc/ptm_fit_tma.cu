@@ -1,9 +1,9 @@
 // K1, streaming form -- the LRGB fit as a persistent, warp-specialised sm_100a kernel.
 //
-//   producer warp : one elected lane feeds a shared-memory ring with 1-D bulk copies
-//                   (cp.async.bulk, SASS UBLKCP): each copy is one light's 3072-byte run of
-//                   1024 consecutive pixels; four lights per stage, four stages in flight,
-//                   completion counted in bytes on an mbarrier per stage.
+//   producer warp : feeds a shared-memory ring with 1-D bulk copies (cp.async.bulk, SASS
+//                   UBLKCP): each copy is one light's 3072-byte run of 1024 consecutive pixels;
+//                   L lights per stage (one producer lane each), S stages, completion counted
+//                   in bytes on an mbarrier per stage.  Default L = 6, S = 4 (72 KB ring).
 //   consumer warps: 8 warps x 32 lanes x 4 pixels = the 1024-pixel tile.  Per light a lane
 //                   reads its 12 bytes as 3 words (lane stride 3 words: conflict free), turns
 //                   the four luma bytes into floats with PRMT + FADD, and issues 24 FFMA
@@ -12,17 +12,21 @@
 //                   `ev += w` (no unpacking at all) and `od += bytes 1,3 as 16-bit lanes`;
 //                   the even-byte sums are recovered at the end as ev - (S1 << 8) - (S3 << 24).
 //   epilogue      : integer mean, JFIF colour conversion, 256 / Y normalisation, running
-//                   extrema, and a per-warp shared-memory transpose so the 96 bytes of float
-//                   coefficients per lane leave as fully coalesced 16-byte stores.
+//                   extrema, and a warp-private staging area laid out like the output so the
+//                   96 + 12 bytes per lane leave as fully coalesced 16-byte stores.
 //
-// HBM latency is covered by the ring (up to 48 KB in flight per CTA, two CTAs per SM), not by
-// occupancy, so the consumers keep their accumulators in registers without spilling.
+// HBM latency is covered by the ring, not by occupancy (two CTAs per SM), so the consumers keep
+// their 24 accumulators in registers without spilling.  Measured on B200 (24 MP x 60 lights):
+// a read-only ring of this shape streams the stack at 7.2 TB/s; with K1's own 27 B/px of output
+// mixed in the floor is 0.77 ms (tools/ubench_read.cu), the kernel runs in 0.83 ms.
 //
 // Reference arithmetic fused here: rti-builder/ptmlib.c:692-725 (fit), :762-802 (average),
 // rti-builder/ptm-encoder.c:327-353 (colour + normalise), rti-builder/ptmlib.c:826-847 (extrema).
 #include "ptm_device.cuh"
 #include "ptm_kernels.h"
 #include "ptm_tma.cuh"
+
+#include <cstdlib>
 
 namespace ptm {
 
@@ -31,18 +35,16 @@ constexpr int kConsumers = kConsumerWarps * 32;          // 256
 constexpr int kTmaThreads = kConsumers + 32;             // + producer warp
 constexpr int kTilePx = kConsumers * 4;                  // 1024
 constexpr int kTileBytes = kTilePx * 3;                  // 3072 per light
-constexpr int kLightsPerStage = 4;
-constexpr int kStages = 4;
-constexpr int kStageBytes = kLightsPerStage * kTileBytes;
-constexpr int kStageWordsPerWarp = 32 * 28 + 32 * 3;     // padded coefficient rows + rgb words
+constexpr int kWarpStageBytes = 128 * 24 + 128 * 3;      // a warp's 128 pixels: float coefficients + colour bytes
 
+// dynamic shared memory: [ring: S stages x L lights x 3072 B][2 S mbarriers][matrix: n x 32 B]
+template <int L, int S>
 struct TmaSmem {
-    // dynamic shared memory layout (all offsets multiples of 16 bytes)
-    static __host__ __device__ size_t ring() { return 0; }
-    static __host__ __device__ size_t staging() { return (size_t) kStages * kStageBytes; }
-    static __host__ __device__ size_t bars() { return staging() + (size_t) kConsumerWarps * kStageWordsPerWarp * 4; }
-    static __host__ __device__ size_t matrix() { return bars() + 2 * kStages * sizeof(uint64_t); }
-    static __host__ __device__ size_t total(unsigned n_lights) { return matrix() + (size_t) n_lights * 32; }
+    static constexpr size_t stage_bytes = (size_t) L * kTileBytes;
+    static constexpr size_t bars = (size_t) S * stage_bytes;
+    static constexpr size_t staging = bars + 2 * S * sizeof(uint64_t);        // 8 warps x (3072 + 384) B
+    static constexpr size_t matrix = staging + (size_t) kConsumerWarps * kWarpStageBytes;
+    static constexpr size_t total(unsigned n_lights) { return matrix + (size_t) n_lights * 32; }
 };
 
 // One light's contribution to a lane's four pixels.
@@ -70,16 +72,18 @@ __device__ __forceinline__ void consume_light(const uint32_t *s32, const float4 
     od[2] += __byte_perm(w2, 0, 0x4341);
 }
 
-template <bool kWriteCoeffs>
+// kDebug (tuning builds only, never selected by default): 1 = consumers skip the arithmetic
+// (ring delivery ceiling), 2 = consumers skip the waits (arithmetic ceiling).
+template <int L, int S, bool kWriteCoeffs, int kDebug = 0>
 __global__ void __launch_bounds__(kTmaThreads, 2)
 fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles) {
+    using Smem = TmaSmem<L, S>;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ int keys_s[2 * PTM_NCOEF];
-    uint8_t *ring = smem + TmaSmem::ring();
-    float *staging = reinterpret_cast<float *>(smem + TmaSmem::staging());
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + TmaSmem::bars());
-    uint64_t *empty = full + kStages;
-    float4 *m_s = reinterpret_cast<float4 *>(smem + TmaSmem::matrix());
+    uint8_t *ring = smem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Smem::bars);
+    uint64_t *empty = full + S;
+    float4 *m_s = reinterpret_cast<float4 *>(smem + Smem::matrix);
 
     const unsigned n = a.n_lights;
     for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
@@ -88,7 +92,7 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles) {
         m_s[2 * i + 1] = make_float4(M[4 * n + i], M[5 * n + i], 0.f, 0.f);
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kConsumerWarps);
         }
@@ -97,34 +101,38 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles) {
     __syncthreads();
 
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned n_chunks = (n + kLightsPerStage - 1) / kLightsPerStage;
+    const unsigned n_chunks = (n + L - 1) / L;
     Extrema ext;
     ext.init();
 
     if (warp == kConsumerWarps) {
         // ------------------------------------------------------------ producer
-        if (lane == 0) {
-            const uint64_t policy = l2_policy_evict_first();
-            unsigned it = 0;
-            for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const uint8_t *src = a.stack + (size_t) tile * kTileBytes;
-                for (unsigned c = 0; c < n_chunks; ++c, ++it) {
-                    const unsigned s = it % kStages, ph = (it / kStages) & 1;
+        // lane 0 owns the barrier protocol; lanes 0..L-1 each issue one light's copy of the stage
+        const uint64_t policy = l2_policy_evict_first();
+        unsigned s = 0, ph = 0;
+        for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint8_t *src = a.stack + (size_t) tile * kTileBytes + (size_t) lane * a.image_stride;
+            for (unsigned c = 0; c < n_chunks; ++c) {
+                const unsigned l0 = c * L;
+                const unsigned cnt = min((unsigned) L, n - l0);
+                if (lane == 0) {
                     mbar_wait(&empty[s], ph ^ 1);
-                    const unsigned l0 = c * kLightsPerStage;
-                    const unsigned cnt = min((unsigned) kLightsPerStage, n - l0);
                     mbar_arrive_expect_tx(&full[s], cnt * kTileBytes);
-                    for (unsigned l = 0; l < cnt; ++l)
-                        bulk_g2s(ring + (size_t) s * kStageBytes + (size_t) l * kTileBytes,
-                                 src + (size_t) (l0 + l) * a.image_stride, kTileBytes, &full[s], policy);
+                }
+                __syncwarp();
+                if (lane < cnt)
+                    bulk_g2s(ring + (size_t) s * Smem::stage_bytes + (size_t) lane * kTileBytes,
+                             src + (size_t) l0 * a.image_stride, kTileBytes, &full[s], policy);
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1;
                 }
             }
         }
     } else {
         // ----------------------------------------------------------- consumers
         const unsigned t = threadIdx.x;  // 0..255, owns pixels 4t..4t+3 of the tile
-        float *stg = staging + (size_t) warp * kStageWordsPerWarp;
-        unsigned it = 0;
+        unsigned s = 0, ph = 0;
         for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             float acc[4][PTM_NCOEF];
 #pragma unroll
@@ -134,16 +142,18 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles) {
                     acc[p][k] = 0.f;
             unsigned ev[3] = {0, 0, 0}, od[3] = {0, 0, 0};
 
-            for (unsigned c = 0; c < n_chunks; ++c, ++it) {
-                const unsigned s = it % kStages, ph = (it / kStages) & 1;
-                mbar_wait(&full[s], ph);
-                const uint32_t *buf = reinterpret_cast<const uint32_t *>(ring + (size_t) s * kStageBytes) + 3 * t;
-                const unsigned l0 = c * kLightsPerStage;
-                const unsigned cnt = min((unsigned) kLightsPerStage, n - l0);
-                if (cnt == kLightsPerStage) {
+            for (unsigned c = 0; c < n_chunks; ++c) {
+                if (kDebug != 2)
+                    mbar_wait(&full[s], ph);
+                const uint32_t *buf = reinterpret_cast<const uint32_t *>(ring + (size_t) s * Smem::stage_bytes) + 3 * t;
+                const unsigned l0 = c * L;
+                const unsigned cnt = min((unsigned) L, n - l0);
+                if (kDebug == 1) {
+                    ev[0] += buf[0];
+                } else if (cnt == L) {
                     // straight-line body: all loads of the stage can be hoisted, adds pair into IADD3
 #pragma unroll
-                    for (unsigned l = 0; l < kLightsPerStage; ++l)
+                    for (unsigned l = 0; l < L; ++l)
                         consume_light(buf + l * (kTileBytes / 4), m_s + 2 * (l0 + l), acc, ev, od);
                 } else {
                     for (unsigned l = 0; l < cnt; ++l)
@@ -152,6 +162,10 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles) {
                 __syncwarp();
                 if (lane == 0)
                     mbar_arrive(&empty[s]);
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
 
             // per-byte sums: odd bytes from the 16-bit lanes, even bytes from the plain word sum
@@ -175,45 +189,70 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles) {
                 ext.add(acc[p]);
             }
 
-            // warp-local transpose through shared memory -> coalesced 16-byte stores
-            const size_t px0 = (size_t) tile * kTilePx + (size_t) warp * 128;  // first pixel of this warp
+            // The lane's 96 bytes of coefficients and 12 of colour go through a warp-private
+            // staging area laid out exactly like the output, so that they leave as fully
+            // coalesced 16-byte stores (512 contiguous bytes per warp instruction).
+            uint8_t *stg = smem + Smem::staging + (size_t) warp * kWarpStageBytes;
+            const size_t wpx = (size_t) tile * kTilePx + (size_t) warp * 128;  // the warp's first pixel
             if (kWriteCoeffs) {
-                float4 *row = reinterpret_cast<float4 *>(stg + lane * 28);
+                float4 *row = reinterpret_cast<float4 *>(stg) + lane * 6;
                 const float *f = &acc[0][0];
 #pragma unroll
                 for (int j = 0; j < 6; ++j)
                     row[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             }
-            uint32_t *rgbw = reinterpret_cast<uint32_t *>(stg + 32 * 28);
+            uint32_t *rgbw = reinterpret_cast<uint32_t *>(stg + 128 * 24);
             rgbw[3 * lane + 0] = out_b[0] | (out_b[1] << 8) | (out_b[2] << 16) | (out_b[3] << 24);
             rgbw[3 * lane + 1] = out_b[4] | (out_b[5] << 8) | (out_b[6] << 16) | (out_b[7] << 24);
             rgbw[3 * lane + 2] = out_b[8] | (out_b[9] << 8) | (out_b[10] << 16) | (out_b[11] << 24);
             __syncwarp();
             if (kWriteCoeffs) {
-                float4 *dst = reinterpret_cast<float4 *>(a.coeffs + px0 * PTM_NCOEF);
+                float4 *dst = reinterpret_cast<float4 *>(a.coeffs + wpx * PTM_NCOEF);
+                const float4 *src = reinterpret_cast<const float4 *>(stg);
 #pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    const unsigned q = lane + 32 * r;  // float4 index within the warp's 192
-                    const unsigned tp = q / 6, j = q - tp * 6;
-                    __stcg(dst + q, *reinterpret_cast<const float4 *>(stg + tp * 28 + j * 4));
-                }
+                for (int r = 0; r < 6; ++r)
+                    __stcg(dst + lane + 32 * r, src[lane + 32 * r]);
             }
             if (lane < 24)
-                __stcg(reinterpret_cast<uint4 *>(a.rgb + px0 * 3) + lane,
-                       *reinterpret_cast<const uint4 *>(rgbw + 4 * lane));
+                __stcg(reinterpret_cast<uint4 *>(a.rgb + wpx * 3) + lane,
+                       reinterpret_cast<const uint4 *>(rgbw)[lane]);
             __syncwarp();
         }
     }
     ext.flush(a.keys, keys_s);
 }
 
-// Number of resident CTAs per SM for the streaming kernel (computed once per launch config).
-static int tma_blocks_per_sm(size_t smem, bool write_coeffs) {
-    int nb = 0;
-    cudaError_t e = write_coeffs
-        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fit_lrgb_u8_tma_kernel<true>, kTmaThreads, smem)
-        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fit_lrgb_u8_tma_kernel<false>, kTmaThreads, smem);
-    return e == cudaSuccess ? nb : 0;
+template <int L, int S, int kDebug = 0>
+static cudaError_t launch_variant(const FitArgs &a, size_t n_tiles, int sm_count, cudaStream_t st) {
+    using Smem = TmaSmem<L, S>;
+    static_assert(L <= 32, "one producer lane per light of a stage");
+    // opt in to > 48 KB of dynamic shared memory and look up residency, once per device
+    static int per_sm_cache[64][2];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return e;
+    if (dev < 0 || dev >= 64)
+        return cudaErrorInvalidDevice;
+    const int wc = a.coeffs != nullptr;
+    auto kern = wc ? fit_lrgb_u8_tma_kernel<L, S, true, kDebug> : fit_lrgb_u8_tma_kernel<L, S, false, kDebug>;
+    if (per_sm_cache[dev][wc] == 0) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Smem::total(257));
+        if (e != cudaSuccess)
+            return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kTmaThreads, Smem::total(257));
+        if (e != cudaSuccess)
+            return e;
+        if (nb < 1)
+            return cudaErrorLaunchOutOfResources;
+        per_sm_cache[dev][wc] = nb;
+    }
+    size_t grid = (size_t) sm_count * per_sm_cache[dev][wc];
+    if (grid > n_tiles)
+        grid = n_tiles;
+    kern<<<(unsigned) grid, kTmaThreads, Smem::total(a.n_lights), st>>>(a, (unsigned) n_tiles);
+    return cudaGetLastError();
 }
 
 // Launches the streaming kernel over the whole 1024-pixel tiles of the slab and returns how many
@@ -225,37 +264,24 @@ cudaError_t launch_fit_lrgb_tma(const FitArgs &a, int sm_count, cudaStream_t st,
     const size_t n_tiles = a.pixels / kTilePx;
     if (!ok || n_tiles == 0 || n_tiles > 0xFFFFFFFFull)
         return cudaSuccess;
-    const size_t smem = TmaSmem::total(a.n_lights);
-    // opt in to > 48 KB of dynamic shared memory and look up residency, once per device
-    static int per_sm_cache[64][2];
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess)
-        return e;
-    const int wc = a.coeffs != nullptr;
-    if (dev < 0 || dev >= 64)
-        return cudaErrorInvalidDevice;
-    if (per_sm_cache[dev][wc] == 0) {
-        e = wc ? cudaFuncSetAttribute(fit_lrgb_u8_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int) TmaSmem::total(257))
-               : cudaFuncSetAttribute(fit_lrgb_u8_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int) TmaSmem::total(257));
-        if (e != cudaSuccess)
-            return e;
-        per_sm_cache[dev][wc] = tma_blocks_per_sm(TmaSmem::total(257), wc);
-        if (per_sm_cache[dev][wc] < 1)
-            return cudaErrorLaunchOutOfResources;
+    static int variant = -1;
+    if (variant < 0) {
+        const char *v = getenv("PTM_TMA_VARIANT");  // tuning aid; the default is what ships
+        variant = v ? atoi(v) : 0;
     }
-    const int per_sm = per_sm_cache[dev][wc];
-    size_t grid = (size_t) sm_count * per_sm;
-    if (grid > n_tiles)
-        grid = n_tiles;
-    if (a.coeffs)
-        fit_lrgb_u8_tma_kernel<true><<<(unsigned) grid, kTmaThreads, smem, st>>>(a, (unsigned) n_tiles);
-    else
-        fit_lrgb_u8_tma_kernel<false><<<(unsigned) grid, kTmaThreads, smem, st>>>(a, (unsigned) n_tiles);
-    *done = n_tiles * kTilePx;
-    return cudaGetLastError();
+    cudaError_t e;
+    switch (variant) {
+    case 1: e = launch_variant<5, 5>(a, n_tiles, sm_count, st); break;
+    case 2: e = launch_variant<3, 8>(a, n_tiles, sm_count, st); break;
+    case 3: e = launch_variant<5, 4>(a, n_tiles, sm_count, st); break;
+    case 4: e = launch_variant<4, 5>(a, n_tiles, sm_count, st); break;
+    case 5: e = launch_variant<8, 3>(a, n_tiles, sm_count, st); break;
+    case 11: e = launch_variant<6, 4, 1>(a, n_tiles, sm_count, st); break;
+    default: e = launch_variant<6, 4>(a, n_tiles, sm_count, st); break;
+    }
+    if (e == cudaSuccess)
+        *done = n_tiles * kTilePx;
+    return e;
 }
 
 }  // namespace ptm
