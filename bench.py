@@ -208,7 +208,7 @@ def run_b200(args):
     P = rows * W
 
     stack = torch.empty((N_LIGHTS, rows, W, 3), dtype=torch.uint8, device="cuda")
-    enc = PtmEncoder(W, rows, M, planes=1)
+    enc = PtmEncoder(W, rows, M, planes=1, keep_coeffs=os.environ.get("PTM_KEEP_COEFFS", "0") == "1")
     enc.ctx.synth(SEED, 0, U8, r0 * W, P, light_q14(L), stack, P * 3)
     torch.cuda.synchronize()
 

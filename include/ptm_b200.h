@@ -120,6 +120,13 @@ int ptmb_minmax (ptmb_ctx_t *ctx, const float *coeffs_dev, size_t pixels, int32_
 int ptmb_quantise (ptmb_ctx_t *ctx, const float *coeffs_dev, size_t pixels, const int32_t *keys_dev,
                    uint8_t *bytes_dev, ptmb_scale_bias_t *sb_dev);
 
+/* K2 for a float plane that is scratch (the fused encode: nobody reads the floats afterwards).
+ * Same bytes as ptmb_quantise, but the plane is walked from its end -- the part K1 wrote last,
+ * still dirty in L2 -- and each line is discarded from L2 after use, so it is never written
+ * back to HBM.  The contents of coeffs_dev are UNDEFINED afterwards. */
+int ptmb_quantise_consume (ptmb_ctx_t *ctx, float *coeffs_dev, size_t pixels, const int32_t *keys_dev,
+                           uint8_t *bytes_dev, ptmb_scale_bias_t *sb_dev);
+
 /* K3: the pixel loop of ptm_write_jpeg (rti-builder/ptmlib.c:553-562,587-621) for `n_dirs`
  * light directions at once.  uv: HOST array of n_dirs (u, v) pairs.  out_dev: uint8
  * [n_dirs][height][width][3], top row first (stored row height-1-y, :587-589).

@@ -49,6 +49,7 @@ _SIGNATURES = {
     "ptmb_lrgb_colour_normalise": ([_vp, _vp, _vp, _sz], _int),
     "ptmb_minmax": ([_vp, _vp, _sz, _vp], _int),
     "ptmb_quantise": ([_vp, _vp, _sz, _vp, _vp, _vp], _int),
+    "ptmb_quantise_consume": ([_vp, _vp, _sz, _vp, _vp, _vp], _int),
     "ptmb_relight_lrgb": ([_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, C.c_uint, _vp], _int),
     "ptmb_relight_rgb": ([_vp, _vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, C.c_uint, _vp], _int),
     "ptmb_synth": ([_vp, _u32, _int, _int, _u32, _sz, C.c_uint, _vp, _vp, _sz], _int),

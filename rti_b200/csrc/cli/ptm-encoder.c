@@ -1,0 +1,245 @@
+/*
+ * ptm-encoder (B200 build) -- same command line as the reference's rti-builder/ptm-encoder.c:
+ *
+ *     ptm-encoder [-f FORMAT] [-l] [-o FILE] [-v] FILENAME.LP
+ *
+ * FILENAME.LP lists "filename u v [w]" lines (paths relative to the .lp file); any line with
+ * fewer than three fields, such as a leading count, is skipped (ref :152-157).  At least 12
+ * images are required (ref :204).  Default format PTM_FORMAT_JPEG_RGB, default output stdout
+ * (ref :120-121).  -v prints the reference's phase lines on stderr (wall-clock milliseconds here;
+ * the reference prints summed CPU time).
+ *
+ * What differs from the reference's main: the decoded stack goes through ONE fused GPU pass
+ * (ptm_encode_stack) instead of fit / average / colour loop / scale, and images are read
+ * through ptm_codec.h (lossless raw container in this image).
+ */
+#define _POSIX_C_SOURCE 200809L
+
+#include <argp.h>
+#include <libgen.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "../../../include/ptmlib.h"
+#include "../ptm_codec.h"
+
+const char *argp_program_version = "PTM Encoder 0.1 (B200)";
+
+static struct argp_option options[] = {
+    { "format",  'f', "FORMAT", 0, "Which PTM format to output (default: PTM_FORMAT_JPEG_RGB).", 0 },
+    { "list",    'l', 0,        0, "List supported PTM formats.",                                0 },
+    { "output",  'o', "FILE",   0, "Output to FILE instead of STDOUT.",                          1 },
+    { "verbose", 'v', 0,        0, "Produce verbose output.",                                    2 },
+    { 0 }
+};
+
+struct arguments {
+    const ptm_format_t *format;
+    const char *filename_lp;
+    const char *filename_ptm;
+    int verbose;
+};
+
+static error_t parse_opt (int key, char *arg, struct argp_state *state) {
+    struct arguments *a = state->input;
+    switch (key) {
+    case 'f':
+        a->format = ptm_get_format (arg);
+        if (a->format == NULL) {
+            fprintf (stderr, "No format by that name: %s\n", arg);
+            exit (0);          /* the reference exits 0 here too (ref :69-72) */
+        }
+        break;
+    case 'l':
+        printf ("Supported formats:\n");
+        for (const ptm_format_t *f = ptm_formats; f->name; ++f)
+            printf ("%s\n", f->name);
+        exit (0);
+    case 'o':
+        a->filename_ptm = arg;
+        break;
+    case 'v':
+        a->verbose = 1;
+        break;
+    case ARGP_KEY_ARG:
+        if (state->arg_num >= 1)
+            argp_usage (state);
+        a->filename_lp = arg;
+        break;
+    case ARGP_KEY_END:
+        if (state->arg_num < 1)
+            argp_usage (state);
+        break;
+    default:
+        return ARGP_ERR_UNKNOWN;
+    }
+    return 0;
+}
+
+static struct argp argp = { options, parse_opt, "FILENAME.LP", "Encode a series of JPEG files into a PTM file.",
+                            NULL, NULL, NULL };
+
+static double now_ms (void) {
+    struct timespec ts;
+    clock_gettime (CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
+}
+
+int main (int argc, char *argv[]) {
+    struct arguments args;
+    args.verbose = 0;
+    args.format = ptm_get_format ("PTM_FORMAT_JPEG_RGB");
+    args.filename_ptm = "-";
+    argp_parse (&argp, argc, argv, 0, 0, &args);
+
+    double t0 = now_ms ();
+
+    FILE *fp_lp = fopen (args.filename_lp, "rb");
+    if (fp_lp == NULL) {
+        fprintf (stderr, "can't open %s\n", args.filename_lp);
+        return 1;
+    }
+    char *lp_copy = strdup (args.filename_lp);
+    const char *dir = dirname (lp_copy);
+
+    ptm_header_t *header = ptm_alloc_header ();
+    header->format = args.format;
+
+    size_t cap = 64, n = 0;
+    decoder_t **decoders = malloc (cap * sizeof (*decoders));
+    ptm_image_dims_t dims0 = { 0, 0, 0 };
+
+    char *line = NULL;
+    size_t len = 0;
+    while (getline (&line, &len, fp_lp) != -1) {
+        char *name = malloc (len + 1);
+        float u = 0.0f, v = 0.0f, w = 0.0f;
+        if (sscanf (line, "%s %f %f %f", name, &u, &v, &w) >= 3) {
+            char *path = malloc (strlen (dir) + strlen (name) + 2);
+            sprintf (path, "%s/%s", dir, name);
+            FILE *fp = fopen (path, "rb");
+            if (fp == NULL) {
+                fprintf (stderr, "can't open %s\n", path);
+                return 1;
+            }
+            free (path);
+            ptm_image_dims_t dims;
+            if (ptm_codec_read_dims (fp, &dims)) {
+                fprintf (stderr, "can't read image header of %s\n", name);
+                return 1;
+            }
+            if (n == 0)
+                dims0 = dims;
+            if (dims.width != dims0.width || dims.height != dims0.height || dims.components != dims0.components) {
+                fprintf (stderr, "%s: all images must have the same size\n", name);   /* ref :238-243 asserts */
+                return 1;
+            }
+            decoder_t *d = calloc (1, sizeof (*d));
+            d->fp = fp;
+            d->filename = name;
+            d->u = u;
+            d->v = v;
+            d->w = w;
+            d->dinfo.output_width = dims.width;
+            d->dinfo.output_height = dims.height;
+            d->dinfo.output_components = (int) dims.components;
+            decoders[n++] = d;
+            if (n >= cap) {
+                cap *= 2;
+                decoders = realloc (decoders, cap * sizeof (*decoders));
+            }
+        } else {
+            free (name);
+        }
+    }
+    free (line);
+    free (lp_copy);
+    fclose (fp_lp);
+
+    if (n < 12) {
+        fprintf (stderr, "not enough jpegs %u < %d\n", (unsigned) n, 12);
+        return 1;
+    }
+    if (args.verbose)
+        fprintf (stderr, "%u JPEGs opened ...\n", (unsigned) n);
+
+    float *M = ptm_svd (decoders, (int) n);
+    if (M == NULL) {
+        fprintf (stderr, "Error in Singular Value Decomposition\n");
+        return 1;
+    }
+    if (args.verbose)
+        fprintf (stderr, "done SVD\n");
+
+    if (dims0.components != 3) {
+        fprintf (stderr, "input images must have 3 components\n");
+        return 1;
+    }
+    ptm_image_info_t info;
+    info.n_decoders = (unsigned int) n;
+    info.width = dims0.width;
+    info.height = dims0.height;
+    info.pixels = info.width * info.height;
+    info.row_stride = info.width * dims0.components;
+    info.decoder_stride = info.height * info.row_stride;
+    header->dimen[0] = info.width;
+    header->dimen[1] = info.height;
+
+    /* decode every image into the stack, bottom row first (ref :245-264) */
+    JSAMPLE *buffer = calloc (n * info.decoder_stride, sizeof (JSAMPLE));
+    int failed = 0;
+    #pragma omp parallel for schedule(dynamic)
+    for (size_t i = 0; i < n; ++i) {
+        unsigned char **rows = calloc (info.height, sizeof (*rows));
+        for (size_t y = 0; y < info.height; ++y)
+            rows[y] = buffer + i * info.decoder_stride + (info.height - y - 1) * info.row_stride;
+        ptm_image_dims_t d = { (unsigned int) info.width, (unsigned int) info.height, dims0.components };
+        if (ptm_codec_read_rows (decoders[i]->fp, &d, rows, (unsigned int) info.height))
+            failed = 1;
+        fclose (decoders[i]->fp);
+        free (rows);
+    }
+    if (failed) {
+        fprintf (stderr, "short read while decoding the input images\n");
+        return 1;
+    }
+    double t1 = now_ms ();
+    if (args.verbose)
+        fprintf (stderr, "time for decoding %u JPEGs = %lums\n", (unsigned) n, (unsigned long) (t1 - t0));
+
+    ptm_block_t *blocks = ptm_alloc_blocks (header);
+    ptm_encode_stack (header, &info, buffer, M, blocks);
+    free (buffer);
+    double t2 = now_ms ();
+    if (args.verbose) {
+        /* the reference prints two lines (fit, scale); the fused pass covers both */
+        fprintf (stderr, "time for ptm_fit_poly_jsample = %lums\n", (unsigned long) (t2 - t1));
+        fprintf (stderr, "time for ptm_scale_coefficients = %lums\n", 0ul);
+    }
+
+    FILE *fp_ptm = stdout;
+    if (strcmp (args.filename_ptm, "-") != 0) {
+        fp_ptm = fopen (args.filename_ptm, "wb");
+        if (fp_ptm == NULL) {
+            fprintf (stderr, "can't open %s\n", args.filename_ptm);
+            return 1;
+        }
+    }
+    ptm_write_ptm (fp_ptm, header, blocks);
+    double t3 = now_ms ();
+    if (args.verbose)
+        fprintf (stderr, "time for ptm_write_ptm = %lums\n", (unsigned long) (t3 - t2));
+    fclose (fp_ptm);
+
+    free (M);
+    ptm_free_blocks (header, blocks);
+    for (size_t i = 0; i < n; ++i) {
+        free (decoders[i]->filename);
+        free (decoders[i]);
+    }
+    free (decoders);
+    free (header);
+    return 0;
+}

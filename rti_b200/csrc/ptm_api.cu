@@ -301,7 +301,16 @@ int ptmb_quantise(ptmb_ctx_t *c, const float *coeffs_dev, size_t pixels, const i
     REQUIRE(c && keys_dev, "NULL argument");
     REQUIRE((coeffs_dev && bytes_dev) || pixels == 0, "NULL argument");
     CK(cudaSetDevice(c->device));
-    CK(ptm::launch_quantise(coeffs_dev, pixels, keys_dev, bytes_dev, sb_dev, c->sm_count, c->stream));
+    CK(ptm::launch_quantise(coeffs_dev, pixels, keys_dev, bytes_dev, sb_dev, false, c->sm_count, c->stream));
+    return 0;
+}
+
+int ptmb_quantise_consume(ptmb_ctx_t *c, float *coeffs_dev, size_t pixels, const int32_t *keys_dev,
+                          uint8_t *bytes_dev, ptmb_scale_bias_t *sb_dev) {
+    REQUIRE(c && keys_dev, "NULL argument");
+    REQUIRE((coeffs_dev && bytes_dev) || pixels == 0, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(ptm::launch_quantise(coeffs_dev, pixels, keys_dev, bytes_dev, sb_dev, true, c->sm_count, c->stream));
     return 0;
 }
 
@@ -529,10 +538,10 @@ int ptmb_encode_host_finish(ptmb_ctx_t *c, const int32_t *keys_dev, uint8_t *con
     const int32_t *keys = keys_dev ? keys_dev : c->keys_dev;
     const size_t pixels = s.pixels, plane_floats = pixels * PTMB_COEFFICIENTS;
     const uint8_t *rgb_dev = s.bytes + pixels * PTMB_COEFFICIENTS * s.planes;
-    for (int b = 0; b < s.planes; ++b)
+    for (int b = s.planes - 1; b >= 0; --b)   // last-written plane first: it is the one still in L2
         CK(ptm::launch_quantise(s.coeffs + b * plane_floats, pixels, keys,
                                 s.bytes + (size_t) b * pixels * PTMB_COEFFICIENTS, b == 0 ? c->sb_dev : nullptr,
-                                c->sm_count, c->stream));
+                                coeffs_host == nullptr, c->sm_count, c->stream));
     for (int b = 0; b < s.planes; ++b)
         CK(cudaMemcpyAsync(blocks_host[b], s.bytes + (size_t) b * pixels * PTMB_COEFFICIENTS,
                            pixels * PTMB_COEFFICIENTS, cudaMemcpyDeviceToHost, c->stream));

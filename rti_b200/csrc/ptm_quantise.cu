@@ -14,6 +14,10 @@ namespace ptm {
 constexpr int kQuantThreads = 384;  // multiple of 3 and of 32
 constexpr int kQuantUnroll = 4;
 
+// kConsume: the float plane is scratch that nobody reads afterwards (the fused encode).  The
+// plane is then walked from its END -- the part K1 wrote last and that is still dirty in L2 --
+// and every 128-byte line is discarded from L2 once read, so it is never written back to HBM.
+template <bool kConsume>
 __global__ void __launch_bounds__(kQuantThreads)
 quantise_kernel(const float *__restrict__ coeffs, size_t n_float4, size_t tail_first, size_t n_floats,
                 const int *__restrict__ keys, uint8_t *__restrict__ bytes, void *sb_out) {
@@ -32,7 +36,15 @@ quantise_kernel(const float *__restrict__ coeffs, size_t n_float4, size_t tail_f
     }
     __syncthreads();
 
-    const int k0 = (4 * (threadIdx.x % 3)) % PTM_NCOEF;  // coefficient of the float4's first lane
+    const float4 *src = reinterpret_cast<const float4 *>(coeffs);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(bytes);
+    const size_t step = (size_t) gridDim.x * kQuantThreads;  // multiple of 3
+    // forward: q = q0 + i * step; consuming: the same set of indices mirrored, q -> n_float4 - 1 - q
+    const size_t q0 = (size_t) blockIdx.x * kQuantThreads + threadIdx.x;
+    // coefficient of the float4's first lane: (4 q) % 6 depends on q % 3 only, and q % 3 is the same
+    // for every index this thread visits (step % 3 == 0)
+    const size_t first = kConsume ? (n_float4 - 1 - q0 % n_float4) : q0;
+    const int k0 = (int) ((4 * (first % 3)) % PTM_NCOEF);
     float inv[4], bias[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -40,34 +52,36 @@ quantise_kernel(const float *__restrict__ coeffs, size_t n_float4, size_t tail_f
         bias[j] = bias_s[(k0 + j) % PTM_NCOEF];
     }
 
-    const float4 *src = reinterpret_cast<const float4 *>(coeffs);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(bytes);
-    const size_t step = (size_t) gridDim.x * kQuantThreads;  // multiple of 3
-    size_t q = (size_t) blockIdx.x * kQuantThreads + threadIdx.x;
-
+    size_t q = q0;
     for (; q + (kQuantUnroll - 1) * step < n_float4; q += kQuantUnroll * step) {
         float4 v[kQuantUnroll];
 #pragma unroll
-        for (int u = 0; u < kQuantUnroll; ++u)
-            v[u] = __ldcs(src + q + u * step);
+        for (int u = 0; u < kQuantUnroll; ++u) {
+            const size_t i = kConsume ? n_float4 - 1 - (q + u * step) : q + u * step;
+            v[u] = kConsume ? __ldcg(src + i) : __ldcs(src + i);
+        }
 #pragma unroll
         for (int u = 0; u < kQuantUnroll; ++u) {
+            const size_t i = kConsume ? n_float4 - 1 - (q + u * step) : q + u * step;
             const unsigned b0 = clip_u8(__fadd_rn(__fmul_rn(v[u].x, inv[0]), bias[0]));
             const unsigned b1 = clip_u8(__fadd_rn(__fmul_rn(v[u].y, inv[1]), bias[1]));
             const unsigned b2 = clip_u8(__fadd_rn(__fmul_rn(v[u].z, inv[2]), bias[2]));
             const unsigned b3 = clip_u8(__fadd_rn(__fmul_rn(v[u].w, inv[3]), bias[3]));
-            __stcs(dst + q + u * step, b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+            __stcs(dst + i, b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+            if (kConsume && (i & 7) == 0 && i + 8 <= n_float4)   // first float4 of a whole 128-byte line
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(src + i) : "memory");
         }
     }
     for (; q < n_float4; q += step) {
-        const float4 v = __ldcs(src + q);
+        const size_t i = kConsume ? n_float4 - 1 - q : q;
+        const float4 v = __ldcs(src + i);
         const unsigned b0 = clip_u8(__fadd_rn(__fmul_rn(v.x, inv[0]), bias[0]));
         const unsigned b1 = clip_u8(__fadd_rn(__fmul_rn(v.y, inv[1]), bias[1]));
         const unsigned b2 = clip_u8(__fadd_rn(__fmul_rn(v.z, inv[2]), bias[2]));
         const unsigned b3 = clip_u8(__fadd_rn(__fmul_rn(v.w, inv[3]), bias[3]));
-        __stcs(dst + q, b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+        __stcs(dst + i, b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
     }
-    // scalar tail (fewer than 4 floats) and unaligned fallbacks
+    // scalar tail (fewer than 4 floats)
     if (blockIdx.x == 0) {
         for (size_t e = tail_first + threadIdx.x; e < n_floats; e += kQuantThreads) {
             const int k = (int) (e % PTM_NCOEF);
@@ -102,7 +116,7 @@ quantise_scalar_kernel(const float *__restrict__ coeffs, size_t n_floats, const 
 }
 
 cudaError_t launch_quantise(const float *coeffs, size_t pixels, const int *keys, uint8_t *bytes, void *sb,
-                            int sm_count, cudaStream_t st) {
+                            bool consume, int sm_count, cudaStream_t st) {
     const size_t n_floats = pixels * PTM_NCOEF;
     const bool aligned = ((uintptr_t) coeffs % 16 == 0) && ((uintptr_t) bytes % 4 == 0);
     if (!aligned) {
@@ -116,7 +130,14 @@ cudaError_t launch_quantise(const float *coeffs, size_t pixels, const int *keys,
     size_t want = (n_float4 + (size_t) kQuantThreads * kQuantUnroll - 1) / ((size_t) kQuantThreads * kQuantUnroll);
     size_t cap = (size_t) sm_count * 5;
     unsigned grid = (unsigned) (want < 1 ? 1 : (want < cap ? want : cap));
-    quantise_kernel<<<grid, kQuantThreads, 0, st>>>(coeffs, n_float4, n_float4 * 4, n_floats, keys, bytes, sb);
+    // The mirrored walk keeps a per-thread coefficient pattern only when the float4 count is a
+    // multiple of 3, and a 128-byte line is read by 8 lanes of ONE warp instruction (so it can be
+    // discarded right after) only when the count is a multiple of 8 and the plane is line aligned:
+    // pixels % 16 == 0.  Anything else takes the plain forward kernel.
+    if (consume && n_float4 % 24 == 0 && n_float4 > 0 && (uintptr_t) coeffs % 128 == 0)
+        quantise_kernel<true><<<grid, kQuantThreads, 0, st>>>(coeffs, n_float4, n_float4 * 4, n_floats, keys, bytes, sb);
+    else
+        quantise_kernel<false><<<grid, kQuantThreads, 0, st>>>(coeffs, n_float4, n_float4 * 4, n_floats, keys, bytes, sb);
     return cudaGetLastError();
 }
 

@@ -484,9 +484,9 @@ void ptm_encode_stack (ptm_header_t *h, const ptm_image_info_t *info, const JSAM
     }
 }
 
-/* the pixel loop of ref :587-621 */
-void ptm_relight (const ptm_header_t *h, ptm_block_t *blocks, float u, float v, JSAMPLE *out) {
-    const float uv[2] = { u, v };
+/* the pixel loop of ref :587-621, for a batch of light directions */
+void ptm_relight_batch (const ptm_header_t *h, ptm_block_t *blocks, const float *uv, unsigned int n_dirs,
+                        JSAMPLE *out) {
     int32_t bias[PTM_COEFFICIENTS];
     for (int i = 0; i < PTM_COEFFICIENTS; ++i)
         bias[i] = h->bias[i];
@@ -496,8 +496,13 @@ void ptm_relight (const ptm_header_t *h, ptm_block_t *blocks, float u, float v, 
         exit (1);
     }
     if (ptmb_relight_host (gpu (), (const uint8_t *const *) blocks, h->format->ptm_blocks, h->dimen[0],
-                           h->dimen[1], h->scale, bias, uv, 1, out))
+                           h->dimen[1], h->scale, bias, uv, n_dirs, out))
         gpu_die ("ptm_relight");
+}
+
+void ptm_relight (const ptm_header_t *h, ptm_block_t *blocks, float u, float v, JSAMPLE *out) {
+    const float uv[2] = { u, v };
+    ptm_relight_batch (h, blocks, uv, 1, out);
 }
 
 /* ref :553-628 -- relight, then hand the raster to the image writer */

@@ -110,9 +110,11 @@ class Context:
     def minmax(self, coeffs, pixels, keys):
         _lib.check(self._lib.ptmb_minmax(self._h, _ptr(coeffs), pixels, _ptr(keys)))
 
-    def quantise(self, coeffs, pixels, keys, out_bytes, scale_bias=None):
-        _lib.check(self._lib.ptmb_quantise(self._h, _ptr(coeffs), pixels, _ptr(keys), _ptr(out_bytes),
-                                           _ptr(scale_bias)))
+    def quantise(self, coeffs, pixels, keys, out_bytes, scale_bias=None, consume=False):
+        """K2.  consume=True: the float plane is scratch and is left undefined (L2 lines are
+        discarded instead of written back)."""
+        fn = self._lib.ptmb_quantise_consume if consume else self._lib.ptmb_quantise
+        _lib.check(fn(self._h, _ptr(coeffs), pixels, _ptr(keys), _ptr(out_bytes), _ptr(scale_bias)))
 
     def relight_lrgb(self, coef, rgb, width, height, scale, bias, uv, out):
         scale = np.ascontiguousarray(scale, dtype=np.float32)

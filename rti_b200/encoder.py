@@ -55,6 +55,7 @@ class PtmEncoder:
         self.rgb = torch.empty((P, 3), dtype=torch.uint8, device=dev) if self.planes == 1 else None
         self.keys = torch.empty(NKEYS, dtype=torch.int32, device=dev)
         self.sb = torch.empty(NKEYS, dtype=torch.int32, device=dev)  # 6 floats + 6 ints, raw
+        self.keep_coeffs = bool(keep_coeffs)
         self.launches_per_encode = 2 + self.planes
 
     def _use_current_stream(self):
@@ -78,9 +79,9 @@ class PtmEncoder:
 
     def quantise(self):
         """K2: scale/bias from the (global) keys, then bytes for every plane."""
-        for b in range(self.planes):
+        for b in reversed(range(self.planes)):   # the plane written last is the one still in L2
             self.ctx.quantise(self.coeffs[b], self.pixels, self.keys, self.coef_bytes[b],
-                              self.sb if b == 0 else None)
+                              self.sb if b == 0 else None, consume=not self.keep_coeffs)
 
     def encode(self, stack):
         self.fit(stack)

@@ -1,0 +1,125 @@
+"""GPU tests of the three command lines (rti_b200/bin/ptm-encoder, ptm-decoder, ptm-exploder)
+against the reference's UNMODIFIED mains (oracle/_ref/ptm-*-ref, built from /root/reference by
+oracle/Makefile; both sides use the same lossless raw image container, so files compare
+byte for byte where the arithmetic is exact)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+BIN = os.path.join(ROOT, "rti_b200", "bin")
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+def have_ref():
+    return all(os.path.exists(os.path.join(REF, "ptm-%s-ref" % n)) for n in ("encoder", "decoder", "exploder"))
+
+
+def write_inputs(oracle, d, stack_stored, lights):
+    names = []
+    for i in range(stack_stored.shape[0]):
+        name = "img%03d.rawj" % i
+        oracle.write_rawj(os.path.join(d, name), stack_stored[i, ::-1])   # files are top row first
+        names.append(name)
+    lp = os.path.join(d, "sample.lp")
+    with open(lp, "w") as fp:
+        fp.write("%d\n" % len(names))
+        for name, (u, v, w) in zip(names, lights):
+            fp.write("%s %.9g %.9g %.9g\n" % (name, u, v, w))
+    return lp
+
+
+def run(cmd, **kw):
+    return subprocess.run(cmd, capture_output=True, env=dict(os.environ, OPENBLAS_NUM_THREADS="1"), **kw)
+
+
+@pytest.mark.parametrize("fmt,mode", [("PTM_FORMAT_LRGB", 0), ("PTM_FORMAT_RGB", 1),
+                                      ("PTM_FORMAT_JPEG_LRGB", 0), ("PTM_FORMAT_JPEG_RGB", 1)])
+def test_encoder_decoder_vs_reference_mains(oracle, dome1, tmp_path, fmt, mode):
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    d = str(tmp_path)
+    W, H = 72, 40
+    stack = oracle.synth_stack(0xC11, mode, W, H, dome1)
+    lp = write_inputs(oracle, d, stack, dome1)
+    mine, ref = os.path.join(d, "mine.ptm"), os.path.join(d, "ref.ptm")
+    r = run([os.path.join(BIN, "ptm-encoder"), "-f", fmt, "-o", mine, "-v", lp])
+    assert r.returncode == 0, r.stderr.decode()
+    assert b"60 JPEGs opened" in r.stderr and b"done SVD" in r.stderr
+    r = run([os.path.join(REF, "ptm-encoder-ref"), "-f", fmt, "-o", ref, lp])
+    assert r.returncode == 0, r.stderr.decode()
+    a, b = open(mine, "rb").read(), open(ref, "rb").read()
+    assert len(a) == len(b)
+    # text header: same lines; scale within float noise, bias within 1
+    def header_lines(blob, n):
+        return blob.split(b"\n", n)[:n]
+    nl = 6 if "JPEG" not in fmt else 14
+    ha, hb = header_lines(a, nl), header_lines(b, nl)
+    assert ha[:4] == hb[:4]
+    np.testing.assert_allclose([float(x) for x in ha[4].split()], [float(x) for x in hb[4].split()], rtol=3e-6, atol=2e-6)
+    assert max(abs(int(x) - int(y)) for x, y in zip(ha[5].split(), hb[5].split())) <= 1
+    assert ha[6:] == hb[6:]
+    if ha[5] == hb[5]:
+        body_a = np.frombuffer(a, np.uint8)[-(len(a) - len(b"\n".join(ha)) - 1):]
+        body_b = np.frombuffer(b, np.uint8)[-(len(b) - len(b"\n".join(hb)) - 1):]
+        diff = np.abs(body_a.astype(int) - body_b.astype(int))
+        print("%s: %d of %d payload bytes differ" % (fmt, (diff != 0).sum(), diff.size))
+        assert diff.max() <= 1 and (diff != 0).mean() < 0.01
+    # decoders: each on the REFERENCE's file must agree exactly (relight is bit exact),
+    for uv in (("0.25", "-0.5"), ()):
+        ra = run([os.path.join(BIN, "ptm-decoder"), ref, *uv])
+        rb = run([os.path.join(REF, "ptm-decoder-ref"), ref, *uv])
+        assert ra.returncode == 0 and rb.returncode == 0, ra.stderr.decode()
+        assert ra.stdout == rb.stdout
+    # and my decoder reads my own file
+    ra = run([os.path.join(BIN, "ptm-decoder"), mine, "0.1", "0.2"])
+    rb = run([os.path.join(REF, "ptm-decoder-ref"), mine, "0.1", "0.2"])
+    assert ra.returncode == 0 and ra.stdout == rb.stdout
+
+
+def test_exploder_vs_reference_main(oracle, dome1, tmp_path):
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    d = str(tmp_path)
+    stack = oracle.synth_stack(0xC12, 0, 48, 36, dome1)
+    lp = write_inputs(oracle, d, stack, dome1)
+    ptm = os.path.join(d, "x.ptm")
+    assert run([os.path.join(REF, "ptm-encoder-ref"), "-f", "PTM_FORMAT_LRGB", "-o", ptm, lp]).returncode == 0
+    os.makedirs(os.path.join(d, "a"))
+    os.makedirs(os.path.join(d, "b"))
+    ra = run([os.path.join(BIN, "ptm-exploder"), ptm, lp, os.path.join(d, "a", "out.jpg")])
+    rb = run([os.path.join(REF, "ptm-exploder-ref"), ptm, lp, os.path.join(d, "b", "out.jpg")])
+    assert ra.returncode == 0 and rb.returncode == 0, ra.stderr.decode()
+    fa, fb = sorted(os.listdir(os.path.join(d, "a"))), sorted(os.listdir(os.path.join(d, "b")))
+    assert fa == fb and len(fa) == 60 and fa[0] == "out001.jpeg"     # ref :71-83 naming, no dash
+    for f in fa:
+        assert open(os.path.join(d, "a", f), "rb").read() == open(os.path.join(d, "b", f), "rb").read(), f
+    assert ra.stderr.replace(b"/a/", b"/b/") == rb.stderr             # the progress lines
+
+
+def test_cli_errors_match_reference(tmp_path):
+    enc = os.path.join(BIN, "ptm-encoder")
+    r = run([enc, "-l"])
+    assert r.returncode == 0 and r.stdout.split() == [b"Supported", b"formats:", b"PTM_FORMAT_RGB", b"PTM_FORMAT_JPEG_RGB",
+                                                      b"PTM_FORMAT_LRGB", b"PTM_FORMAT_JPEG_LRGB", b"PTM_FORMAT_LUM"]
+    r = run([enc, "-f", "NOPE", "x.lp"])
+    assert r.returncode == 0 and b"No format by that name: NOPE" in r.stderr
+    r = run([enc, os.path.join(str(tmp_path), "missing.lp")])
+    assert r.returncode == 1 and b"can't open" in r.stderr
+    lp = tmp_path / "few.lp"
+    lp.write_text("0\n")
+    r = run([enc, str(lp)])
+    assert r.returncode == 1 and b"not enough jpegs 0 < 12" in r.stderr
+    r = run([os.path.join(BIN, "ptm-decoder")])
+    assert r.returncode == 1 and b"Usage:" in r.stderr
+    bad = tmp_path / "bad.ptm"
+    bad.write_text("hello\n")
+    r = run([os.path.join(BIN, "ptm-decoder"), str(bad)])
+    assert r.returncode == 1 and b"not a PTM file" in r.stderr
+    r = run([os.path.join(BIN, "ptm-exploder"), "a", "b"])
+    assert r.returncode == 1 and b"Usage:" in r.stderr

@@ -374,3 +374,31 @@ def test_full_size_properties(ctx, oracle, dome1, M60):
     q = (want_c * inv).astype(np.float32) + bias.astype(np.float32)
     want_b = np.where(q > 255, 255, np.where(q < 0, 0, q)).astype(np.uint8)
     assert_bytes_close(enc.coef_bytes[0].reshape(H, W, 6)[rows].cpu().numpy(), want_b, "24 MP sampled rows")
+
+
+def test_consuming_quantise_gives_identical_bytes(ctx, oracle, dome1, M60):
+    """ptmb_quantise_consume (mirrored walk + L2 discard) must produce the same bytes as ptmb_quantise."""
+    stack = oracle.synth_stack(41, 0, 512, 300, dome1)     # pixels % 16 == 0 -> the consuming kernel runs
+    P = 512 * 300
+    ctx.set_matrix(M60)
+    coeffs = torch.empty((P, 6), dtype=torch.float32, device="cuda")
+    rgb = torch.empty((P, 3), dtype=torch.uint8, device="cuda")
+    keys = torch.empty(12, dtype=torch.int32, device="cuda")
+    a = torch.empty((P, 6), dtype=torch.uint8, device="cuda")
+    b = torch.empty((P, 6), dtype=torch.uint8, device="cuda")
+    ctx.keys_init(keys)
+    ctx.fit_lrgb(dev(stack), P * 3, P, coeffs, rgb, keys)
+    ctx.quantise(coeffs, P, keys, a)
+    ctx.quantise(coeffs, P, keys, b, consume=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    # odd sizes fall back to the forward kernel and still agree
+    P2 = 333 * 7
+    c2 = torch.randn((P2, 6), device="cuda") * 100
+    ctx.keys_init(keys)
+    ctx.minmax(c2, P2, keys)
+    a2 = torch.empty((P2, 6), dtype=torch.uint8, device="cuda")
+    b2 = torch.empty((P2, 6), dtype=torch.uint8, device="cuda")
+    ctx.quantise(c2, P2, keys, a2)
+    ctx.quantise(c2.clone(), P2, keys, b2, consume=True)
+    assert torch.equal(a2, b2)

@@ -1,0 +1,64 @@
+"""GPU tests of the ptmlib.h-shaped host API (rti_b200/ptmlib.py -> libptm.so): the reference's
+own call sequence, step by step, with host buffers."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_call_sequence_lrgb(oracle, dome1):
+    from rti_b200 import ptmlib as P
+    W, H = 90, 41
+    stack = oracle.synth_stack(0xAB1, 0, W, H, dome1)
+    M = P.ptm_svd(dome1)
+    np.testing.assert_array_equal(M, oracle.pinv(dome1))            # same LAPACKE path on the host
+    info = P.image_info(W, H, 60)
+    hdr = P.ptm_alloc_header("PTM_FORMAT_LRGB", W, H)
+    blocks = P.ptm_alloc_blocks(hdr)
+    # rti-builder/ptm-encoder.c:313-353,406
+    coeffs = P.ptm_fit_poly_jsample(info, stack, 3, M)
+    ycc = P.ptm_cbcr_avg(info, stack)
+    np.testing.assert_array_equal(ycc.reshape(H, W, 3), oracle.chroma_avg(stack))
+    P.ptm_lrgb_finish(info, ycc, coeffs)
+    blocks[1][:] = ycc
+    P.ptm_scale_coefficients(hdr, coeffs, blocks)
+    want = oracle.encode_lrgb(stack, M)
+    np.testing.assert_array_equal(blocks[1].reshape(H, W, 3), want["rgb"])
+    np.testing.assert_allclose(np.array(hdr.scale), want["scale"], rtol=2e-6)
+    assert np.abs(np.array(hdr.bias) - want["bias"]).max() <= 1
+    d = np.abs(blocks[0].reshape(H, W, 6).astype(int) - want["coef"].astype(int))
+    assert d.max() <= 1 and (d != 0).mean() < 0.01
+    # the fused entry gives the same blocks as the step-by-step sequence
+    hdr2 = P.ptm_alloc_header("PTM_FORMAT_LRGB", W, H)
+    blocks2 = P.ptm_alloc_blocks(hdr2)
+    P.ptm_encode_stack(hdr2, info, stack, M, blocks2)
+    np.testing.assert_array_equal(blocks2[0], blocks[0])
+    np.testing.assert_array_equal(blocks2[1], blocks[1])
+    assert list(hdr2.bias) == list(hdr.bias) and list(hdr2.scale) == list(hdr.scale)
+    # relight through the header (scale goes through %f in a real file; here it is the float itself)
+    out = P.ptm_relight(hdr, blocks, 0.3, 0.1)
+    ref = oracle.relight_lrgb(blocks[0].reshape(H, W, 6), blocks[1].reshape(H, W, 3), np.array(hdr.scale, np.float32),
+                              np.array(hdr.bias, np.int32), 0.3, 0.1)
+    np.testing.assert_array_equal(out, ref)
+
+
+def test_reference_call_sequence_rgb_and_uint(oracle, dome1):
+    from rti_b200 import ptmlib as P
+    W, H = 34, 27
+    stack = oracle.synth_stack(0xAB2, 1, W, H, dome1)
+    M = P.ptm_svd(dome1)
+    info = P.image_info(W, H, 60)
+    hdr = P.ptm_alloc_header("PTM_FORMAT_RGB", W, H)
+    blocks = P.ptm_alloc_blocks(hdr)
+    # rti-builder/ptm-encoder.c:272-284: one fit per channel with buffer + r, stride 3
+    coeffs = np.stack([P.ptm_fit_poly_jsample(info, stack, 3, M, channel=r) for r in range(3)])
+    P.ptm_scale_coefficients(hdr, coeffs, blocks)
+    want = oracle.encode_rgb(stack, M)
+    np.testing.assert_allclose(np.array(hdr.scale), want["scale"], rtol=2e-6)
+    d = np.abs(np.stack(blocks).reshape(3, H, W, 6).astype(int) - want["coef"].astype(int))
+    assert d.max() <= 1 and (d != 0).mean() < 0.02
+    # ptm_fit_poly_uint (rti-builder/ptmlib.c:727): unsigned int samples, stride 1
+    L = stack.astype(np.uint32).sum(-1, dtype=np.uint32)[..., None]          # LUM() of ptmlib.h:160
+    got = P.ptm_fit_poly_uint(P.image_info(W, H, 60, 1), L, 1, M)
+    want_u = oracle.fit_u32(np.ascontiguousarray(L), M)
+    np.testing.assert_allclose(got.reshape(H, W, 6), want_u, rtol=0, atol=2e-2)
