@@ -138,6 +138,11 @@ int ptmb_relight_rgb (ptmb_ctx_t *ctx, const uint8_t *r_dev, const uint8_t *g_de
                       size_t width, size_t height, const float *scale, const int32_t *bias,
                       const float *uv, unsigned n_dirs, uint8_t *out_dev);
 
+/* Self test of K3's arithmetic shortcuts: compares the 3-instruction x / 255.0f and the CLIP
+ * replacement with the IEEE division / the reference's CLIP (rti-builder/ptmlib.h:156-158) for
+ * the float bit patterns [first_bits, first_bits + count); *mismatches must come back 0. */
+int ptmb_selftest_div255 (ptmb_ctx_t *ctx, uint64_t first_bits, uint64_t count, uint64_t *mismatches);
+
 /* Synthetic stack for pixels [pixel0, pixel0 + pixels) of every light, generated on the
  * device (integer only; the host statement is oracle/synth.c).  lights_q14: HOST array of
  * n_lights (x, y, z) in Q14. */

@@ -380,6 +380,26 @@ int ptmb_relight_rgb(ptmb_ctx_t *c, const uint8_t *r_dev, const uint8_t *g_dev, 
     return relight_common(c, a, false, width, height, scale, bias, uv, n_dirs, out_dev);
 }
 
+int ptmb_selftest_div255(ptmb_ctx_t *c, uint64_t first_bits, uint64_t count, uint64_t *mismatches) {
+    REQUIRE(c && mismatches, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    unsigned long long *dev = nullptr;
+    CK(cudaMalloc(&dev, sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(dev, 0, sizeof(unsigned long long), c->stream);
+    if (e == cudaSuccess)
+        e = ptm::launch_div255_selftest(first_bits, count, dev, c->sm_count, c->stream);
+    unsigned long long host = 0;
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(&host, dev, sizeof(host), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->stream);
+    cudaFree(dev);
+    if (e != cudaSuccess)
+        return fail("ptmb_selftest_div255", cudaGetErrorString(e));
+    *mismatches = host;
+    return 0;
+}
+
 int ptmb_synth(ptmb_ctx_t *c, uint32_t seed, int mode, int sample_type, uint32_t pixel0, size_t pixels,
                unsigned n_lights, const int32_t *lights_q14, void *stack_dev, size_t image_stride) {
     REQUIRE(c && lights_q14 && (stack_dev || pixels == 0), "NULL argument");

@@ -47,6 +47,8 @@ cudaError_t launch_minmax(const float *coeffs, size_t pixels, int *keys, int sm_
 cudaError_t launch_quantise(const float *coeffs, size_t pixels, const int *keys, uint8_t *bytes, void *sb,
                             bool consume, int sm_count, cudaStream_t st);
 cudaError_t launch_relight(const RelightArgs &a, bool lrgb, int sm_count, cudaStream_t st);
+cudaError_t launch_div255_selftest(unsigned long long first, unsigned long long count,
+                                   unsigned long long *mismatches_dev, int sm_count, cudaStream_t st);
 cudaError_t launch_synth(uint32_t seed, int mode, int sample_type, uint32_t pixel0, size_t pixels,
                          unsigned n_lights, const int32_t *lights_q14_dev, void *stack, size_t image_stride,
                          int sm_count, cudaStream_t st);

@@ -131,6 +131,12 @@ class Context:
                                               scale.ctypes.data, bias.ctypes.data, uv.ctypes.data, uv.shape[0],
                                               _ptr(out)))
 
+    def selftest_div255(self, first_bits=0, count=1 << 32):
+        """Mismatch count of K3's division / CLIP shortcuts against IEEE / the reference."""
+        n = C.c_uint64(0)
+        _lib.check(self._lib.ptmb_selftest_div255(self._h, first_bits, count, C.byref(n)))
+        return n.value
+
     def synth(self, seed, mode, sample_type, pixel0, pixels, lights_q14, stack, image_stride):
         lq = np.ascontiguousarray(lights_q14, dtype=np.int32).reshape(-1, 3)
         _lib.check(self._lib.ptmb_synth(self._h, seed, mode, sample_type, pixel0, pixels, lq.shape[0],

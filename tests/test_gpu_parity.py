@@ -402,3 +402,39 @@ def test_consuming_quantise_gives_identical_bytes(ctx, oracle, dome1, M60):
     ctx.quantise(c2, P2, keys, a2)
     ctx.quantise(c2.clone(), P2, keys, b2, consume=True)
     assert torch.equal(a2, b2)
+
+
+def test_relight_shortcuts_are_exact_for_every_finite_float(ctx):
+    """x / 255.0f as multiply + two FMAs, and CLIP as min/max + add-round-toward-zero, compared with
+    the IEEE division and the reference's CLIP for every finite float (both signs, denormals
+    included).  Only +-inf differs (NaN instead of inf)."""
+    assert ctx.selftest_div255(0x00000000, 0x7F800000) == 0
+    assert ctx.selftest_div255(0x80000000, 0x7F800000) == 0
+    assert ctx.selftest_div255(0x7F800000, 1) == 1
+
+
+def test_relight_sweep_360_directions(ctx, oracle, dome1, M60):
+    """BASELINE.json configs[4] shape at small size: 360 directions on a ring of radius 0.7,
+    batched in one call; every raster equals the oracle."""
+    W, H = 64, 36
+    stack = oracle.synth_stack(51, 0, W, H, dome1)
+    enc = oracle.encode_lrgb(stack, M60)
+    scale = oracle.header_roundtrip(enc["scale"])
+    th = np.deg2rad(np.arange(360, dtype=np.float64))
+    uv = np.stack([0.7 * np.cos(th), 0.7 * np.sin(th)], 1).astype(np.float32)
+    out = torch.empty((360, H, W, 3), dtype=torch.uint8, device="cuda")
+    ctx.relight_lrgb(dev(enc["coef"]), dev(enc["rgb"]), W, H, scale, enc["bias"], uv, out)
+    got = out.cpu().numpy()
+    for i in range(0, 360, 7):
+        np.testing.assert_array_equal(got[i], oracle.relight_lrgb(enc["coef"], enc["rgb"], scale, enc["bias"],
+                                                                  float(uv[i, 0]), float(uv[i, 1])))
+    # odd width -> generic kernel, same answer
+    W2 = 37
+    st2 = oracle.synth_stack(52, 0, W2, 9, dome1)
+    e2 = oracle.encode_lrgb(st2, M60)
+    out2 = torch.empty((3, 9, W2, 3), dtype=torch.uint8, device="cuda")
+    ctx.relight_lrgb(dev(e2["coef"]), dev(e2["rgb"]), W2, 9, e2["scale"], e2["bias"], uv[:3], out2)
+    for i in range(3):
+        np.testing.assert_array_equal(out2.cpu().numpy()[i],
+                                      oracle.relight_lrgb(e2["coef"], e2["rgb"], e2["scale"], e2["bias"],
+                                                          float(uv[i, 0]), float(uv[i, 1])))
