@@ -86,6 +86,18 @@ struct Extrema {
             mx[k] = fmaxf(mx[k], c[k]);
         }
     }
+    // four pixels at once with the 3-input min / max of sm_100 (FMNMX3): 2 instructions per
+    // coefficient and bound instead of 4.  Like fminf / fmaxf, NaN operands are ignored.
+    __device__ __forceinline__ void add4(const float (&c)[4][PTM_NCOEF]) {
+#pragma unroll
+        for (int k = 0; k < PTM_NCOEF; ++k) {
+            float a, b;
+            asm("min.f32 %0, %1, %2, %3;" : "=f"(a) : "f"(mn[k]), "f"(c[0][k]), "f"(c[1][k]));
+            asm("min.f32 %0, %1, %2, %3;" : "=f"(mn[k]) : "f"(a), "f"(c[2][k]), "f"(c[3][k]));
+            asm("max.f32 %0, %1, %2, %3;" : "=f"(b) : "f"(mx[k]), "f"(c[0][k]), "f"(c[1][k]));
+            asm("max.f32 %0, %1, %2, %3;" : "=f"(mx[k]) : "f"(b), "f"(c[2][k]), "f"(c[3][k]));
+        }
+    }
     // warp shuffle tree, then one atomicMax per warp and coefficient on the keys
     __device__ __forceinline__ void flush(int *keys, int *smem_keys /* [12] in shared memory */) {
         // block-level merge in shared memory first, then 12 global atomics per block

@@ -74,9 +74,14 @@ __device__ __forceinline__ void consume_light(const uint32_t *s32, const float4 
 
 // kDebug (tuning builds only, never selected by default): 1 = consumers skip the arithmetic
 // (ring delivery ceiling), 2 = consumers skip the waits (arithmetic ceiling).
-template <int L, int S, bool kWriteCoeffs, int kDebug = 0>
+// kFull: the light count is a multiple of L, so every stage is complete (no per-stage count).
+__device__ __forceinline__ unsigned tile_px_of(unsigned tile, unsigned n_tiles, unsigned tail_px) {
+    return (tail_px && tile + 1 == n_tiles) ? tail_px : (unsigned) kTilePx;
+}
+
+template <int L, int S, bool kWriteCoeffs, bool kFull, int kDebug = 0>
 __global__ void __launch_bounds__(kTmaThreads, 2)
-fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles) {
+fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
     using Smem = TmaSmem<L, S>;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ int keys_s[2 * PTM_NCOEF];
@@ -112,17 +117,19 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles) {
         unsigned s = 0, ph = 0;
         for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const uint8_t *src = a.stack + (size_t) tile * kTileBytes + (size_t) lane * a.image_stride;
+            // the last tile may be partial (tail_px pixels, a multiple of 16 => bytes a multiple of 16)
+            const unsigned bytes = (tail_px && tile + 1 == n_tiles) ? tail_px * 3 : (unsigned) kTileBytes;
             for (unsigned c = 0; c < n_chunks; ++c) {
                 const unsigned l0 = c * L;
-                const unsigned cnt = min((unsigned) L, n - l0);
+                const unsigned cnt = kFull ? (unsigned) L : min((unsigned) L, n - l0);
                 if (lane == 0) {
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full[s], cnt * kTileBytes);
+                    mbar_arrive_expect_tx(&full[s], cnt * bytes);
                 }
                 __syncwarp();
                 if (lane < cnt)
                     bulk_g2s(ring + (size_t) s * Smem::stage_bytes + (size_t) lane * kTileBytes,
-                             src + (size_t) l0 * a.image_stride, kTileBytes, &full[s], policy);
+                             src + (size_t) l0 * a.image_stride, bytes, &full[s], policy);
                 if (++s == S) {
                     s = 0;
                     ph ^= 1;
@@ -147,7 +154,7 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles) {
                     mbar_wait(&full[s], ph);
                 const uint32_t *buf = reinterpret_cast<const uint32_t *>(ring + (size_t) s * Smem::stage_bytes) + 3 * t;
                 const unsigned l0 = c * L;
-                const unsigned cnt = min((unsigned) L, n - l0);
+                const unsigned cnt = kFull ? (unsigned) L : min((unsigned) L, n - l0);
                 if (kDebug == 1) {
                     ev[0] += buf[0];
                 } else if (cnt == L) {
@@ -186,14 +193,18 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles) {
                 const unsigned cba = div_magic(sum[3 * p + 1], a.magic);
                 const unsigned cra = div_magic(sum[3 * p + 2], a.magic);
                 lrgb_finish(ya, cba, cra, acc[p], out_b[3 * p], out_b[3 * p + 1], out_b[3 * p + 2]);
-                ext.add(acc[p]);
             }
+            if (4 * t < tile_px_of(tile, n_tiles, tail_px))   // lanes past a partial tile hold stale bytes
+                ext.add4(acc);
 
             // The lane's 96 bytes of coefficients and 12 of colour go through a warp-private
             // staging area laid out exactly like the output, so that they leave as fully
             // coalesced 16-byte stores (512 contiguous bytes per warp instruction).
             uint8_t *stg = smem + Smem::staging + (size_t) warp * kWarpStageBytes;
             const size_t wpx = (size_t) tile * kTilePx + (size_t) warp * 128;  // the warp's first pixel
+            // pixels of this warp that exist (all 128 except in a partial last tile; multiple of 16)
+            const unsigned tile_px = (tail_px && tile + 1 == n_tiles) ? tail_px : (unsigned) kTilePx;
+            const unsigned valid = min(128u, tile_px > warp * 128 ? tile_px - warp * 128 : 0u);
             if (kWriteCoeffs) {
                 float4 *row = reinterpret_cast<float4 *>(stg) + lane * 6;
                 const float *f = &acc[0][0];
@@ -211,9 +222,10 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles) {
                 const float4 *src = reinterpret_cast<const float4 *>(stg);
 #pragma unroll
                 for (int r = 0; r < 6; ++r)
-                    __stcg(dst + lane + 32 * r, src[lane + 32 * r]);
+                    if (lane + 32 * r < valid * 6 / 4)
+                        __stcg(dst + lane + 32 * r, src[lane + 32 * r]);
             }
-            if (lane < 24)
+            if (lane < valid * 3 / 16)
                 __stcg(reinterpret_cast<uint4 *>(a.rgb + wpx * 3) + lane,
                        reinterpret_cast<const uint4 *>(rgbw)[lane]);
             __syncwarp();
@@ -223,11 +235,11 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles) {
 }
 
 template <int L, int S, int kDebug = 0>
-static cudaError_t launch_variant(const FitArgs &a, size_t n_tiles, int sm_count, cudaStream_t st) {
+static cudaError_t launch_variant(const FitArgs &a, size_t n_tiles, unsigned tail_px, int sm_count, cudaStream_t st) {
     using Smem = TmaSmem<L, S>;
     static_assert(L <= 32, "one producer lane per light of a stage");
     // opt in to > 48 KB of dynamic shared memory and look up residency, once per device
-    static int per_sm_cache[64][2];
+    static int per_sm_cache[64][4];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess)
@@ -235,8 +247,11 @@ static cudaError_t launch_variant(const FitArgs &a, size_t n_tiles, int sm_count
     if (dev < 0 || dev >= 64)
         return cudaErrorInvalidDevice;
     const int wc = a.coeffs != nullptr;
-    auto kern = wc ? fit_lrgb_u8_tma_kernel<L, S, true, kDebug> : fit_lrgb_u8_tma_kernel<L, S, false, kDebug>;
-    if (per_sm_cache[dev][wc] == 0) {
+    const bool full = a.n_lights % L == 0;
+    auto kern = wc ? (full ? fit_lrgb_u8_tma_kernel<L, S, true, true, kDebug> : fit_lrgb_u8_tma_kernel<L, S, true, false, kDebug>)
+                   : (full ? fit_lrgb_u8_tma_kernel<L, S, false, true, kDebug> : fit_lrgb_u8_tma_kernel<L, S, false, false, kDebug>);
+    const int slot = wc * 2 + (full ? 1 : 0);
+    if (per_sm_cache[dev][slot] == 0) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Smem::total(257));
         if (e != cudaSuccess)
             return e;
@@ -246,12 +261,12 @@ static cudaError_t launch_variant(const FitArgs &a, size_t n_tiles, int sm_count
             return e;
         if (nb < 1)
             return cudaErrorLaunchOutOfResources;
-        per_sm_cache[dev][wc] = nb;
+        per_sm_cache[dev][slot] = nb;
     }
-    size_t grid = (size_t) sm_count * per_sm_cache[dev][wc];
+    size_t grid = (size_t) sm_count * per_sm_cache[dev][slot];
     if (grid > n_tiles)
         grid = n_tiles;
-    kern<<<(unsigned) grid, kTmaThreads, Smem::total(a.n_lights), st>>>(a, (unsigned) n_tiles);
+    kern<<<(unsigned) grid, kTmaThreads, Smem::total(a.n_lights), st>>>(a, (unsigned) n_tiles, tail_px);
     return cudaGetLastError();
 }
 
@@ -261,7 +276,12 @@ cudaError_t launch_fit_lrgb_tma(const FitArgs &a, int sm_count, cudaStream_t st,
     *done = 0;
     const bool ok = a.n_lights <= 257 && ((uintptr_t) a.stack % 16 == 0) && (a.image_stride % 16 == 0) &&
                     ((uintptr_t) a.rgb % 16 == 0) && (a.coeffs == nullptr || (uintptr_t) a.coeffs % 16 == 0);
-    const size_t n_tiles = a.pixels / kTilePx;
+    // whole 1024-pixel tiles, plus the remainder as one partial tile when its byte count keeps
+    // the 16-byte granularity of bulk copies (remainder % 16 == 0)
+    const size_t full_tiles = a.pixels / kTilePx;
+    const unsigned rem = (unsigned) (a.pixels % kTilePx);
+    const unsigned tail_px = (rem % 16 == 0) ? rem : 0;
+    const size_t n_tiles = full_tiles + (tail_px ? 1 : 0);
     if (!ok || n_tiles == 0 || n_tiles > 0xFFFFFFFFull)
         return cudaSuccess;
     static int variant = -1;
@@ -271,16 +291,16 @@ cudaError_t launch_fit_lrgb_tma(const FitArgs &a, int sm_count, cudaStream_t st,
     }
     cudaError_t e;
     switch (variant) {
-    case 1: e = launch_variant<5, 5>(a, n_tiles, sm_count, st); break;
-    case 2: e = launch_variant<3, 8>(a, n_tiles, sm_count, st); break;
-    case 3: e = launch_variant<5, 4>(a, n_tiles, sm_count, st); break;
-    case 4: e = launch_variant<4, 5>(a, n_tiles, sm_count, st); break;
-    case 5: e = launch_variant<8, 3>(a, n_tiles, sm_count, st); break;
-    case 11: e = launch_variant<6, 4, 1>(a, n_tiles, sm_count, st); break;
-    default: e = launch_variant<6, 4>(a, n_tiles, sm_count, st); break;
+    case 1: e = launch_variant<5, 5>(a, n_tiles, tail_px, sm_count, st); break;
+    case 2: e = launch_variant<3, 8>(a, n_tiles, tail_px, sm_count, st); break;
+    case 3: e = launch_variant<5, 4>(a, n_tiles, tail_px, sm_count, st); break;
+    case 4: e = launch_variant<4, 5>(a, n_tiles, tail_px, sm_count, st); break;
+    case 5: e = launch_variant<8, 3>(a, n_tiles, tail_px, sm_count, st); break;
+    case 11: e = launch_variant<6, 4, 1>(a, n_tiles, tail_px, sm_count, st); break;
+    default: e = launch_variant<6, 4>(a, n_tiles, tail_px, sm_count, st); break;
     }
     if (e == cudaSuccess)
-        *done = n_tiles * kTilePx;
+        *done = full_tiles * kTilePx + tail_px;
     return e;
 }
 
