@@ -64,6 +64,8 @@ def lib():
     L.orc_relight_lrgb.restype = None
     L.orc_relight_rgb.argtypes = [_u8p, _u8p, _u8p, C.c_size_t, C.c_size_t, _f32p, _i32p, C.c_float, C.c_float, _u8p]
     L.orc_relight_rgb.restype = None
+    L.orc_lrgb16_finish.argtypes = [_u16p, C.c_size_t, C.c_uint, _f32p, _u8p]
+    L.orc_lrgb16_finish.restype = None
     L.orc_normal.argtypes = [_f32p, _f32p, _f32p, _f32p]
     L.orc_normal.restype = None
     L.orc_blas_corename.restype = C.c_char_p
@@ -185,6 +187,26 @@ def encode_lrgb(stack, M, blas=False):
     lrgb_colour_normalise(rgb, coeffs)
     blocks, sc, bi, mm = scale(coeffs.reshape(-1, NCOEF), 1)
     return dict(coeffs=coeffs, coef=blocks[0].reshape(H, W, NCOEF), rgb=rgb, scale=sc, bias=bi, minmax=mm)
+
+
+def encode_lrgb_u16(stack, M):
+    """EXTENSION (no reference counterpart, see orc_lrgb16_finish): 16-bit LRGB encode."""
+    n, H, W, _ = stack.shape
+    coeffs = fit_u32(stack.astype(np.uint32), M, 0)
+    rgb = np.zeros((H, W, 3), np.uint8)
+    lib().orc_lrgb16_finish(np.ascontiguousarray(stack).reshape(-1), H * W, n, coeffs.reshape(-1), rgb.reshape(-1))
+    blocks, sc, bi, mm = scale(coeffs.reshape(-1, NCOEF), 1)
+    return dict(coeffs=coeffs, coef=blocks[0].reshape(H, W, NCOEF), rgb=rgb, scale=sc, bias=bi, minmax=mm)
+
+
+def encode_rgb_u16(stack, M):
+    """RGB-format encode of a 16-bit stack through the reference's > 8 bit entry
+    (ptm_fit_poly_uint semantics, rti-builder/ptmlib.c:727-760) and ptm_scale_coefficients."""
+    n, H, W, _ = stack.shape
+    s32 = stack.astype(np.uint32)
+    coeffs = np.stack([fit_u32(s32, M, ch) for ch in range(3)], axis=0)
+    blocks, sc, bi, mm = scale(coeffs.reshape(3, -1, NCOEF), 3)
+    return dict(coeffs=coeffs, coef=blocks.reshape(3, H, W, NCOEF), scale=sc, bias=bi, minmax=mm)
 
 
 def encode_rgb(stack, M, blas=False):

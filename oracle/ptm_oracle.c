@@ -370,6 +370,35 @@ void orc_encode_rgb (const uint8_t *stack, size_t width, size_t height, unsigned
     orc_scale (coeffs, pixels, 3, scale, bias, blocks, minmax_out);
 }
 
+/* EXTENSION -- 16-bit LRGB.  The reference has no such path (its ptm_cbcr_avg and colour loop
+ * are 8 bit only), so this has NO reference to be pinned against; it states the semantics the
+ * CUDA path implements: fit on the 16-bit luma exactly like ptm_fit_poly_uint
+ * (rti-builder/ptmlib.c:727-760), truncated integer means at 16 bits (same formula as :774-800),
+ * the colour conversion of rti-builder/ptm-encoder.c:331-339 on their top 8 bits, and
+ * norm = 256 / (16-bit mean luma).  stack: uint16 [n][pixels][3]. */
+void orc_lrgb16_finish (const uint16_t *stack, size_t pixels, unsigned n_lights, float *coeffs, uint8_t *rgb) {
+    #pragma omp parallel for schedule(static)
+    for (size_t p = 0; p < pixels; ++p) {
+        unsigned int s0 = 0, s1 = 0, s2 = 0;
+        for (unsigned n = 0; n < n_lights; ++n) {
+            const uint16_t *t = stack + ((size_t) n * pixels + p) * 3;
+            s0 += t[0];
+            s1 += t[1];
+            s2 += t[2];
+        }
+        const unsigned ya = s0 / n_lights, cba = s1 / n_lights, cra = s2 / n_lights;
+        float y = (float) (ya >> 8);
+        float cb = (int) (cba >> 8) - 128;
+        float cr = (int) (cra >> 8) - 128;
+        rgb[p * 3 + 0] = clip_u8 (y + 1.40200f * cr);
+        rgb[p * 3 + 1] = clip_u8 (y - 0.34414f * cb - 0.71414f * cr);
+        rgb[p * 3 + 2] = clip_u8 (y + 1.77200f * cb);
+        float norm = 256.0f / (float) ya;
+        for (int k = 0; k < NCOEF; ++k)
+            coeffs[p * NCOEF + k] *= norm;
+    }
+}
+
 /* rti-builder/ptmlib.c:808-814 (ptm_normal), including its sign quirk in the
  * last line (1 - nu^2 + nv^2). */
 void orc_normal (const float *c, float *nu, float *nv, float *nw) {

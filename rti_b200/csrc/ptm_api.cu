@@ -234,9 +234,10 @@ int ptmb_fit_lrgb(ptmb_ctx_t *c, const void *stack_dev, int sample_type, size_t 
     ptm::FitArgs a;
     if (make_fit_args(c, stack_dev, image_stride, pixels, a))
         return 1;
-    REQUIRE(sample_type == PTMB_U8, "LRGB fit takes uint8 stacks (the reference's ptm_cbcr_avg is 8 bit only)");
+    REQUIRE(sample_type == PTMB_U8 || sample_type == PTMB_U16, "LRGB fit takes uint8 or uint16 stacks");
+    REQUIRE(c->n_lights <= 65536 || sample_type == PTMB_U8, "too many lights for 16-bit sums");
     REQUIRE(rgb_dev && keys_dev, "rgb / keys output is NULL");
-    REQUIRE(image_stride >= pixels * 3, "image_stride smaller than one image");
+    REQUIRE(image_stride >= pixels * 3 * sample_size(sample_type), "image_stride smaller than one image");
     a.coeffs = coeffs_dev;
     a.rgb = rgb_dev;
     a.keys = keys_dev;
@@ -453,7 +454,7 @@ int ptmb_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, int sample_type,
     REQUIRE(c && stack_host && M, "NULL argument");
     REQUIRE(format_planes == 1 || format_planes == 3, "format_planes must be 1 (LRGB) or 3 (RGB)");
     const size_t ss = sample_size(sample_type);
-    REQUIRE(ss == 1 || (ss == 2 && format_planes == 3), "unsupported sample type for this format");
+    REQUIRE(ss == 1 || ss == 2, "host encode takes uint8 or uint16 stacks");
     const size_t pixels = width * height;
     REQUIRE(pixels > 0, "empty image");
     if (ptmb_set_matrix(c, M, n_lights))

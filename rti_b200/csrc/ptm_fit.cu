@@ -113,7 +113,16 @@ fit_lrgb_u8_kernel(FitArgs a) {
 template <typename T>
 __global__ void __launch_bounds__(kFitThreads)
 fit_lrgb_generic_kernel(FitArgs a, size_t first_pixel) {
+    // 16-bit stacks (no counterpart in the reference, whose ptm_cbcr_avg is 8 bit only): the fit
+    // runs on the 16-bit luma exactly like ptm_fit_poly_uint, the means are taken at 16 bits, the
+    // colour conversion uses their top 8 bits, and the normalisation is 256 / (16-bit mean luma),
+    // which yields the same dimensionless coefficients as the 8-bit path.
+    constexpr int kShift = sizeof(T) == 2 ? 8 : 0;
+    extern __shared__ float m_gen[];  // [n][6]
     __shared__ int keys_s[2 * PTM_NCOEF];
+    for (unsigned i = threadIdx.x; i < a.n_lights * PTM_NCOEF; i += blockDim.x)
+        m_gen[i] = a.M[(size_t) (i % PTM_NCOEF) * a.n_lights + i / PTM_NCOEF];
+    __syncthreads();
     Extrema ext;
     ext.init();
     const size_t count = a.pixels - first_pixel;
@@ -122,19 +131,30 @@ fit_lrgb_generic_kernel(FitArgs a, size_t first_pixel) {
         const size_t p = first_pixel + i;
         float acc[PTM_NCOEF] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         unsigned s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll 4
         for (unsigned n = 0; n < a.n_lights; ++n) {
             const T *t = reinterpret_cast<const T *>(a.stack + (size_t) n * a.image_stride) + p * 3;
-            const unsigned v0 = t[0], v1 = t[1], v2 = t[2];
+            const unsigned v0 = __ldg(t), v1 = __ldg(t + 1), v2 = __ldg(t + 2);
             const float y = (float) v0;
 #pragma unroll
             for (int k = 0; k < PTM_NCOEF; ++k)
-                acc[k] = fmaf(a.M[(size_t) k * a.n_lights + n], y, acc[k]);
+                acc[k] = fmaf(m_gen[n * PTM_NCOEF + k], y, acc[k]);
             s0 += v0;
             s1 += v1;
             s2 += v2;
         }
+        const unsigned ya = s0 / a.n_lights, cba = s1 / a.n_lights, cra = s2 / a.n_lights;
         unsigned r, g, b;
-        lrgb_finish(s0 / a.n_lights, s1 / a.n_lights, s2 / a.n_lights, acc, r, g, b);
+        if (kShift == 0) {
+            lrgb_finish(ya, cba, cra, acc, r, g, b);
+        } else {
+            float scratch[PTM_NCOEF] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            lrgb_finish(ya >> kShift, cba >> kShift, cra >> kShift, scratch, r, g, b);   // colour only
+            const float norm = __fdiv_rn(256.0f, (float) ya);
+#pragma unroll
+            for (int k = 0; k < PTM_NCOEF; ++k)
+                acc[k] = __fmul_rn(acc[k], norm);
+        }
         ext.add(acc);
         if (a.coeffs) {
 #pragma unroll
@@ -225,7 +245,11 @@ fit_rgb_u8_kernel(FitArgs a) {
 template <typename T>
 __global__ void __launch_bounds__(kFitThreads)
 fit_rgb_generic_kernel(FitArgs a, size_t first_pixel) {
+    extern __shared__ float m_gen[];  // [n][6]
     __shared__ int keys_s[2 * PTM_NCOEF];
+    for (unsigned i = threadIdx.x; i < a.n_lights * PTM_NCOEF; i += blockDim.x)
+        m_gen[i] = a.M[(size_t) (i % PTM_NCOEF) * a.n_lights + i / PTM_NCOEF];
+    __syncthreads();
     Extrema ext;
     ext.init();
     const size_t count = (a.pixels - first_pixel) * 3;
@@ -234,12 +258,13 @@ fit_rgb_generic_kernel(FitArgs a, size_t first_pixel) {
         const size_t p = first_pixel + i / 3;
         const unsigned ch = (unsigned) (i % 3);
         float acc[PTM_NCOEF] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
         for (unsigned n = 0; n < a.n_lights; ++n) {
             const T *t = reinterpret_cast<const T *>(a.stack + (size_t) n * a.image_stride) + p * 3 + ch;
-            const float v = (float) (unsigned) t[0];
+            const float v = (float) (unsigned) __ldg(t);
 #pragma unroll
             for (int k = 0; k < PTM_NCOEF; ++k)
-                acc[k] = fmaf(a.M[(size_t) k * a.n_lights + n], v, acc[k]);
+                acc[k] = fmaf(m_gen[n * PTM_NCOEF + k], v, acc[k]);
         }
         if (ch == 0)
             ext.add(acc);
@@ -345,8 +370,14 @@ cudaError_t launch_keys_init(int *keys, cudaStream_t st) {
 cudaError_t launch_fit_lrgb(const FitArgs &a, int sample_type, int sm_count, cudaStream_t st) {
     if (a.pixels == 0)
         return cudaSuccess;
-    if (sample_type != 0)
+    if (sample_type != 0 && sample_type != 1)
         return cudaErrorInvalidValue;
+    const size_t gen_smem = (size_t) a.n_lights * PTM_NCOEF * sizeof(float);
+    if (sample_type == 1) {   // 16-bit stacks: generic kernel only (not tuned in this round)
+        const unsigned grid = grid_for(a.pixels, kFitThreads, sm_count, 8);
+        fit_lrgb_generic_kernel<uint16_t><<<grid, kFitThreads, gen_smem, st>>>(a, 0);
+        return cudaGetLastError();
+    }
     // 1) whole 1024-pixel tiles through the streaming (bulk copy) kernel when the layout allows it
     size_t done = 0;
     cudaError_t e = launch_fit_lrgb_tma(a, sm_count, st, &done);
@@ -368,7 +399,7 @@ cudaError_t launch_fit_lrgb(const FitArgs &a, int sample_type, int sm_count, cud
     // 3) whatever is left (tile / group remainders, unaligned stacks, > 257 lights): one pixel per thread
     if (done < a.pixels) {
         const unsigned grid = grid_for(a.pixels - done, kFitThreads, sm_count, 8);
-        fit_lrgb_generic_kernel<uint8_t><<<grid, kFitThreads, 0, st>>>(a, done);
+        fit_lrgb_generic_kernel<uint8_t><<<grid, kFitThreads, gen_smem, st>>>(a, done);
     }
     return cudaGetLastError();
 }
@@ -388,10 +419,11 @@ cudaError_t launch_fit_rgb(const FitArgs &a, int sample_type, int sm_count, cuda
     }
     if (done < a.pixels) {
         const unsigned grid = grid_for((a.pixels - done) * 3, kFitThreads, sm_count, 8);
+        const size_t gen_smem = (size_t) a.n_lights * PTM_NCOEF * sizeof(float);
         if (sample_type == 0)
-            fit_rgb_generic_kernel<uint8_t><<<grid, kFitThreads, 0, st>>>(a, done);
+            fit_rgb_generic_kernel<uint8_t><<<grid, kFitThreads, gen_smem, st>>>(a, done);
         else if (sample_type == 1)
-            fit_rgb_generic_kernel<uint16_t><<<grid, kFitThreads, 0, st>>>(a, done);
+            fit_rgb_generic_kernel<uint16_t><<<grid, kFitThreads, gen_smem, st>>>(a, done);
         else
             return cudaErrorInvalidValue;
     }

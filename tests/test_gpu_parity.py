@@ -438,3 +438,50 @@ def test_relight_sweep_360_directions(ctx, oracle, dome1, M60):
         np.testing.assert_array_equal(out2.cpu().numpy()[i],
                                       oracle.relight_lrgb(e2["coef"], e2["rgb"], e2["scale"], e2["bias"],
                                                           float(uv[i, 0]), float(uv[i, 1])))
+
+
+def test_sixteen_bit_stacks(ctx, oracle):
+    """BASELINE.json configs[3] shape at small size: 100 lights, 16-bit linear samples, RGB-format
+    PTM (reference semantics: ptm_fit_poly_uint + ptm_scale_coefficients) and LRGB (extension, no
+    reference counterpart: checked against the oracle's statement of the same semantics)."""
+    from rti_b200 import lights
+    from rti_b200.device import U16
+    L = lights.dome100_lights()
+    M = oracle.pinv(L)
+    W, H = 40, 26
+    P = W * H
+    ctx.set_matrix(M)
+    keys = torch.empty(12, dtype=torch.int32, device="cuda")
+    sb = torch.empty(12, dtype=torch.int32, device="cuda")
+    # RGB format
+    s16 = oracle.synth_stack(0x5EED0004, 1, W, H, L, dtype=np.uint16)
+    want = oracle.encode_rgb_u16(s16, M)
+    d16 = dev(s16.view(np.int16)).view(torch.uint16)
+    coeffs = torch.empty((3, P, 6), dtype=torch.float32, device="cuda")
+    coef = torch.empty((3, P, 6), dtype=torch.uint8, device="cuda")
+    ctx.keys_init(keys)
+    ctx.fit_rgb(d16, P * 6, P, coeffs, P * 6, keys, U16)
+    for b in range(3):
+        ctx.quantise(coeffs[b], P, keys, coef[b], sb if b == 0 else None)
+    raw = sb.cpu().numpy()
+    for ch in range(3):
+        assert coeff_error(coeffs[ch].cpu().numpy().reshape(H, W, 6), want["coeffs"][ch], M, s16[..., ch]) <= 1e-5
+    np.testing.assert_allclose(raw[:6].view(np.float32), want["scale"], rtol=2e-6)
+    assert np.abs(raw[6:].astype(int) - want["bias"].astype(int)).max() <= 1
+    if np.array_equal(raw[6:], want["bias"]):
+        assert_bytes_close(coef.cpu().numpy().reshape(3, H, W, 6), want["coef"], "16-bit RGB coefficient bytes", 0.02)
+    # host-buffer entry with a 16-bit stack
+    g = ctx.encode_host(s16, M, planes=3)
+    np.testing.assert_array_equal(np.stack(g["blocks"]).reshape(3, P, 6), coef.cpu().numpy())
+    # LRGB (extension)
+    y16 = oracle.synth_stack(0x5EED0005, 0, W, H, L, dtype=np.uint16)
+    want = oracle.encode_lrgb_u16(y16, M)
+    c1 = torch.empty((P, 6), dtype=torch.float32, device="cuda")
+    rgb = torch.empty((P, 3), dtype=torch.uint8, device="cuda")
+    ctx.keys_init(keys)
+    ctx.fit_lrgb(dev(y16.view(np.int16)).view(torch.uint16), P * 6, P, c1, rgb, keys, U16)
+    np.testing.assert_array_equal(rgb.cpu().numpy().reshape(H, W, 3), want["rgb"])
+    got = c1.cpu().numpy().reshape(H, W, 6)
+    norm = 256.0 / np.floor(y16[..., 0].astype(np.float64).sum(0) / 100)
+    bound = np.einsum("kn,nhw->hwk", np.abs(M).astype(np.float64), y16[..., 0].astype(np.float64)) * norm[..., None]
+    assert (np.abs(got - want["coeffs"]) / bound).max() <= 1e-5
