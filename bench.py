@@ -208,7 +208,8 @@ def run_b200(args):
     P = rows * W
 
     stack = torch.empty((N_LIGHTS, rows, W, 3), dtype=torch.uint8, device="cuda")
-    enc = PtmEncoder(W, rows, M, planes=1, keep_coeffs=os.environ.get("PTM_KEEP_COEFFS", "1") == "1")
+    enc = PtmEncoder(W, rows, M, planes=1, keep_coeffs=os.environ.get("PTM_KEEP_COEFFS", "1") == "1",
+                     exchange=os.environ.get("PTM_EXCHANGE", "p2p"))
     enc.ctx.synth(SEED, 0, U8, r0 * W, P, light_q14(L), stack, P * 3)
     torch.cuda.synchronize()
 
@@ -312,7 +313,9 @@ def run_b200(args):
                                % (W, H, N_LIGHTS, world),
                    "rows_per_gpu": rows, "l2": "inputs larger than L2 (%.0f MB stack per GPU, streamed once per step)"
                                                % (stack.numel() / 1e6),
-                   "exchange": "none" if world == 1 else "int32 MAX all-reduce of 12 keys (NCCL)"},
+                   "exchange": {"none": "none", "nccl": "int32 MAX all-reduce of 12 keys (NCCL)",
+                                "p2p": "12 int32 keys through NVLink peer-memory mailboxes (2 one-block kernels)"}
+                               [enc.exchange_kind]},
         "roofline": {"bound": "hbm", "kernel": "fit_lrgb_u8 (K1)", "achieved": k1_gbs, "peak": peak, "unit": "GB/s",
                      "frac": k1_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_px": ALG_BYTES_K1, "k1_ms": k1_ms,

@@ -169,6 +169,22 @@ int ptmb_encode_host (ptmb_ctx_t *ctx, const void *stack_host, int sample_type, 
                       float *coeffs_host, ptmb_scale_bias_t *sb_host);
 int ptmb_encode_host_release (ptmb_ctx_t *ctx);
 
+/* Cross-GPU merge of the extrema keys over NVLink peer memory, one process per GPU -- the one
+ * exchange step of the path, 48 bytes, latency bound.  Each rank creates a mailbox
+ * and exports a 64-byte IPC handle; the hosts swap handles out of band (any transport), every
+ * rank connects, and ptmb_xchg_allreduce_max then replaces keys_dev by the element-wise maximum
+ * over all ranks with two one-block kernels around plain peer stores: stream ordered, no host
+ * synchronisation, no collective library.  Integer max on order-preserving keys is exact, so the
+ * result is bit-identical on every rank.  An int32 MAX all-reduce of the same 12 values through
+ * NCCL / MPI is an equivalent alternative (rti_b200/encoder.py falls back to it). */
+#define PTMB_XCHG_HANDLE_BYTES 64
+typedef struct ptmb_xchg ptmb_xchg_t;
+int ptmb_xchg_create (ptmb_ctx_t *ctx, int rank, int world, ptmb_xchg_t **xchg, void *handle_out);
+int ptmb_xchg_connect (ptmb_xchg_t *xchg, const void *handles /* world x 64 bytes, rank order */);
+int ptmb_xchg_allreduce_max (ptmb_ctx_t *ctx, ptmb_xchg_t *xchg, int32_t *keys_dev);
+int ptmb_xchg_status (ptmb_ctx_t *ctx, ptmb_xchg_t *xchg, int *status);
+void ptmb_xchg_destroy (ptmb_xchg_t *xchg);
+
 /* Host-pointer forms of the individual steps, for callers that keep the reference's own
  * call sequence through ptmlib.h (each streams its operands through device slabs):
  *   ptmb_fit_channel_host            ptm_fit_poly_jsample / _uint   rti-builder/ptmlib.c:692-760

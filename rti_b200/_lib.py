@@ -58,6 +58,11 @@ _SIGNATURES = {
     "ptmb_encode_host_finish": ([_vp, _vp, C.POINTER(_vp), _vp, _vp], _int),
     "ptmb_encode_host_release": ([_vp], _int),
     "ptmb_encode_host": ([_vp, _vp, _int, _sz, _sz, C.c_uint, _vp, _int, C.POINTER(_vp), _vp, _vp], _int),
+    "ptmb_xchg_create": ([_vp, _int, _int, C.POINTER(_vp), _vp], _int),
+    "ptmb_xchg_connect": ([_vp, _vp], _int),
+    "ptmb_xchg_allreduce_max": ([_vp, _vp, _vp], _int),
+    "ptmb_xchg_status": ([_vp, _vp, C.POINTER(C.c_int)], _int),
+    "ptmb_xchg_destroy": ([_vp], None),
     "ptmb_fit_channel_host": ([_vp, _vp, _int, _sz, _sz, _sz, C.c_uint, _vp, _vp], _int),
     "ptmb_chroma_avg_host": ([_vp, _vp, _sz, C.c_uint, _vp], _int),
     "ptmb_lrgb_colour_normalise_host": ([_vp, _vp, _vp, _sz], _int),

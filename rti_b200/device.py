@@ -185,6 +185,48 @@ class Context:
         _lib.check(self._lib.ptmb_encode_host_release(self._h))
 
 
+class KeyExchange:
+    """NVLink peer-memory merge of the extrema keys (ptmb_xchg_* in include/ptm_b200.h).
+
+    Two-step set-up so that every rank can take part in the out-of-band handle swap even if
+    its own step failed: ``create`` -> handle bytes (or raises), the host all-gathers the
+    handles with any transport, ``connect(list_of_handles)`` maps the peers."""
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, ctx, rank, world):
+        self._lib = ctx._lib
+        self._ctx = ctx
+        self.world = world
+        self._h = C.c_void_p()
+        handle = (C.c_char * self.HANDLE_BYTES)()
+        _lib.check(self._lib.ptmb_xchg_create(ctx._h, rank, world, C.byref(self._h), handle))
+        self.handle = bytes(handle)
+
+    def connect(self, handles):
+        assert len(handles) == self.world and all(len(h) == self.HANDLE_BYTES for h in handles)
+        _lib.check(self._lib.ptmb_xchg_connect(self._h, b"".join(handles)))
+
+    def allreduce_max(self, keys):
+        _lib.check(self._lib.ptmb_xchg_allreduce_max(self._ctx._h, self._h, _ptr(keys)))
+
+    def status(self):
+        st = C.c_int(0)
+        _lib.check(self._lib.ptmb_xchg_status(self._ctx._h, self._h, C.byref(st)))
+        return st.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ptmb_xchg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def light_q14(lights):
     """Q14 fixed-point light directions for the synthetic generator (round half away)."""
     l = np.asarray(lights, dtype=np.float32).reshape(-1, 3) * np.float32(16384.0)

@@ -16,7 +16,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .device import NCOEF, NKEYS, U8, U16, Context, key_to_float
+from .device import NCOEF, NKEYS, U8, U16, Context, KeyExchange, key_to_float
 
 
 def slab_rows(height, world_size, rank):
@@ -34,12 +34,48 @@ def allreduce_keys(keys, group=None):
     return keys
 
 
+def make_key_exchange(ctx, group=None):
+    """Set up the NVLink peer-memory exchange for the ranks of `group`; returns None (and every
+    rank agrees on None) if any rank could not map its peers, so callers fall back to NCCL."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2:
+        return None
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    # every rank takes part in both collectives below whatever happened locally, so a failure
+    # on one rank can never leave the others waiting
+    xch = None
+    try:
+        xch = KeyExchange(ctx, rank, world)
+        mine = xch.handle
+    except Exception:
+        mine = b""
+    handles = [None] * world
+    dist.all_gather_object(handles, mine, group=group)
+    ok = 1
+    if xch is None or any(len(h) != KeyExchange.HANDLE_BYTES for h in handles):
+        ok = 0
+    else:
+        try:
+            xch.connect(handles)
+        except Exception:
+            ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:
+        if xch is not None:
+            xch.close()
+        return None
+    return xch
+
+
 class PtmEncoder:
     """LRGB (planes=1) or RGB-format (planes=3) encoder for one row slab held in HBM.
 
-    stack: CUDA uint8 tensor [n_lights, rows, width, 3] (stored row order)."""
+    stack: CUDA uint8 tensor [n_lights, rows, width, 3] (stored row order).
+    exchange: "p2p" (NVLink peer-memory mailboxes, falling back to NCCL if peers cannot be
+    mapped), or "nccl" (int32 MAX all-reduce through torch.distributed)."""
 
-    def __init__(self, width, rows, M, planes=1, device=None, group=None, keep_coeffs=True):
+    def __init__(self, width, rows, M, planes=1, device=None, group=None, keep_coeffs=True, exchange="p2p"):
         assert torch.cuda.is_available(), "rti_b200 needs a CUDA device (no CPU fallback)"
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.width, self.rows, self.planes = int(width), int(rows), int(planes)
@@ -56,7 +92,12 @@ class PtmEncoder:
         self.keys = torch.empty(NKEYS, dtype=torch.int32, device=dev)
         self.sb = torch.empty(NKEYS, dtype=torch.int32, device=dev)  # 6 floats + 6 ints, raw
         self.keep_coeffs = bool(keep_coeffs)
-        self.launches_per_encode = 2 + self.planes
+        self.xchg = make_key_exchange(self.ctx, group) if exchange == "p2p" else None
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.exchange_kind = "none" if not multi else ("p2p" if self.xchg is not None else "nccl")
+        # keys-init, K1, K2 per plane (+ publish and gather kernels of the peer exchange)
+        self.launches_per_encode = 2 + self.planes + (2 if self.xchg is not None else 0)
 
     def _use_current_stream(self):
         self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
@@ -75,7 +116,10 @@ class PtmEncoder:
             self.ctx.fit_rgb(stack, image_stride, self.pixels, self.coeffs, self.pixels * NCOEF, self.keys, st)
 
     def exchange(self):
-        allreduce_keys(self.keys, self.group)
+        if self.xchg is not None:
+            self.xchg.allreduce_max(self.keys)
+        else:
+            allreduce_keys(self.keys, self.group)
 
     def quantise(self):
         """K2: scale/bias from the (global) keys, then bytes for every plane."""

@@ -1,0 +1,77 @@
+"""Multi-GPU test (needs >= 2 GPUs; skipped otherwise): two ranks, row slabs of one image, the
+peer-memory key exchange and the NCCL all-reduce give the same keys, and the sharded blocks are
+byte-identical to the single-GPU encode."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, H, W, ret):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from oracle import oracle as O
+    from rti_b200 import lights
+    from rti_b200.encoder import PtmEncoder, slab_rows
+    L = lights.dome1_lights()
+    M = O.pinv(L)
+    r0, r1 = slab_rows(H, world, rank)
+    slab = torch.from_numpy(O.synth_stack(0xD157, 0, W, H, L, row0=r0, rows=r1 - r0)).cuda()
+    out = {}
+    for kind in ("p2p", "nccl"):
+        enc = PtmEncoder(W, r1 - r0, M, exchange=kind)
+        for _ in range(3):                       # several epochs through the mailboxes
+            enc.encode(slab)
+        torch.cuda.synchronize()
+        status = enc.xchg.status() if enc.xchg is not None else 0
+        out[kind] = (enc.exchange_kind, status, enc.keys.cpu().numpy(), enc.coef_bytes[0].cpu().numpy(),
+                     enc.rgb.cpu().numpy())
+    ret[rank] = (r0, r1, out)
+    dist.destroy_process_group()
+
+
+def test_two_gpu_slabs_equal_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    H, W, world = 301, 128, 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), H, W, ret), nprocs=world, join=True)
+    from oracle import oracle as O
+    from rti_b200 import lights
+    from rti_b200.encoder import PtmEncoder
+    L = lights.dome1_lights()
+    M = O.pinv(L)
+    torch.cuda.set_device(0)
+    full = PtmEncoder(W, H, M)
+    full.encode(torch.from_numpy(O.synth_stack(0xD157, 0, W, H, L)).cuda())
+    torch.cuda.synchronize()
+    kinds = {ret[r][2]["p2p"][0] for r in range(world)}
+    print("exchange used:", kinds)
+    for kind in ("p2p", "nccl"):
+        for r in range(world):
+            assert ret[r][2][kind][1] == 0
+            np.testing.assert_array_equal(ret[r][2][kind][2], full.keys.cpu().numpy())
+        coef = np.concatenate([ret[r][2][kind][3] for r in range(world)])
+        rgb = np.concatenate([ret[r][2][kind][4] for r in range(world)])
+        np.testing.assert_array_equal(coef, full.coef_bytes[0].cpu().numpy())
+        np.testing.assert_array_equal(rgb, full.rgb.cpu().numpy())
