@@ -185,6 +185,20 @@ int ptmb_xchg_allreduce_max (ptmb_ctx_t *ctx, ptmb_xchg_t *xchg, int32_t *keys_d
 int ptmb_xchg_status (ptmb_ctx_t *ctx, ptmb_xchg_t *xchg, int *status);
 void ptmb_xchg_destroy (ptmb_xchg_t *xchg);
 
+/* Whole device-resident LRGB encode of one row slab in TWO launches (what the benchmark times):
+ * K1's last block hands the merged keys straight to the mailbox of every rank (its own when
+ * xchg is NULL) and K2 picks them up in its prologue -- no keys-init, no exchange kernels, no
+ * host synchronisation.  Falls back to the separate-kernel sequence for layouts the streaming
+ * kernel does not take.  Call sequence replaced: rti-builder/ptm-encoder.c:313-353,406. */
+int ptmb_encode_lrgb_dev (ptmb_ctx_t *ctx, ptmb_xchg_t *xchg, const void *stack_dev, int sample_type,
+                          size_t image_stride, size_t pixels, float *coeffs_dev, uint8_t *rgb_dev,
+                          uint8_t *coef_bytes_dev, ptmb_scale_bias_t *sb_dev);
+
+/* Timing probes for benchmarks: the next `pairs` ptmb_encode_lrgb_dev calls bracket their fit
+ * stage with CUDA events on the context's stream; _read synchronises and returns milliseconds. */
+int ptmb_probe_arm (ptmb_ctx_t *ctx, unsigned pairs);
+int ptmb_probe_read (ptmb_ctx_t *ctx, float *ms_out, unsigned pairs, unsigned *recorded);
+
 /* Host-pointer forms of the individual steps, for callers that keep the reference's own
  * call sequence through ptmlib.h (each streams its operands through device slabs):
  *   ptmb_fit_channel_host            ptm_fit_poly_jsample / _uint   rti-builder/ptmlib.c:692-760

@@ -63,6 +63,9 @@ _SIGNATURES = {
     "ptmb_xchg_allreduce_max": ([_vp, _vp, _vp], _int),
     "ptmb_xchg_status": ([_vp, _vp, C.POINTER(C.c_int)], _int),
     "ptmb_xchg_destroy": ([_vp], None),
+    "ptmb_encode_lrgb_dev": ([_vp, _vp, _vp, _int, _sz, _sz, _vp, _vp, _vp, _vp], _int),
+    "ptmb_probe_arm": ([_vp, C.c_uint], _int),
+    "ptmb_probe_read": ([_vp, _vp, C.c_uint, C.POINTER(C.c_uint)], _int),
     "ptmb_fit_channel_host": ([_vp, _vp, _int, _sz, _sz, _sz, C.c_uint, _vp, _vp], _int),
     "ptmb_chroma_avg_host": ([_vp, _vp, _sz, C.c_uint, _vp], _int),
     "ptmb_lrgb_colour_normalise_host": ([_vp, _vp, _vp, _sz], _int),

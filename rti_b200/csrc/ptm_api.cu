@@ -7,6 +7,7 @@
 
 #include "../../include/ptm_b200.h"
 #include "ptm_device.cuh"
+#include "ptm_internal.h"
 #include "ptm_kernels.h"
 
 namespace {
@@ -36,38 +37,6 @@ size_t sample_size(int sample_type) {
 }
 
 }  // namespace
-
-struct EncodeScratch {
-    void *stage[2] = {nullptr, nullptr};
-    size_t stage_bytes = 0;
-    float *coeffs = nullptr;
-    size_t coeff_floats = 0;
-    uint8_t *bytes = nullptr;  // planes * pixels * 6 (+ pixels * 3 for LRGB)
-    size_t out_bytes = 0;
-    cudaStream_t copy = nullptr;
-    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
-    size_t pixels = 0;
-    int planes = 0;
-    bool valid = false;
-};
-
-struct ptmb_ctx {
-    EncodeScratch enc;
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    int sm_count = 0;
-    std::vector<float> M_host;
-    float *M_dev = nullptr;
-    unsigned n_lights = 0;
-    unsigned magic = 0;
-    int *keys_dev = nullptr;                 // scratch for the host-buffer entry points
-    ptmb_scale_bias_t *sb_dev = nullptr;
-    std::vector<float> light_host;
-    float *light_dev = nullptr;
-    size_t light_cap = 0;
-    int32_t *lq_dev = nullptr;
-    size_t lq_cap = 0;
-};
 
 extern "C" {
 
@@ -105,6 +74,18 @@ int ptmb_create(int device, void *stream, ptmb_ctx_t **out) {
     cudaError_t e = cudaMalloc(&c->keys_dev, PTMB_KEYS * sizeof(int));
     if (e == cudaSuccess)
         e = cudaMalloc(&c->sb_dev, sizeof(ptmb_scale_bias_t));
+    if (e == cudaSuccess)
+        e = cudaMalloc(&c->ticket_dev, sizeof(unsigned));
+    if (e == cudaSuccess)
+        e = cudaMemset(c->ticket_dev, 0, sizeof(unsigned));
+    if (e == cudaSuccess)
+        e = cudaMalloc(&c->mailbox_dev, ptm::XchgLayout::bytes);
+    if (e == cudaSuccess)
+        e = cudaMemset(c->mailbox_dev, 0, ptm::XchgLayout::bytes);
+    if (e == cudaSuccess)
+        e = ptm::launch_keys_init(c->keys_dev, c->stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) {
         delete c;
         return fail("cudaMalloc", cudaGetErrorString(e));
@@ -124,6 +105,10 @@ void ptmb_destroy(ptmb_ctx_t *c) {
     cudaFree(c->M_dev);
     cudaFree(c->keys_dev);
     cudaFree(c->sb_dev);
+    cudaFree(c->ticket_dev);
+    cudaFree(c->mailbox_dev);
+    for (cudaEvent_t ev : c->probe_events)
+        cudaEventDestroy(ev);
     cudaFree(c->light_dev);
     cudaFree(c->lq_dev);
     delete c;
@@ -226,6 +211,7 @@ static int make_fit_args(ptmb_ctx_t *c, const void *stack_dev, size_t image_stri
     a.plane_stride = 0;
     a.rgb = nullptr;
     a.keys = nullptr;
+    a.handoff = ptm::KeyHandoff{};
     return 0;
 }
 
@@ -302,7 +288,8 @@ int ptmb_quantise(ptmb_ctx_t *c, const float *coeffs_dev, size_t pixels, const i
     REQUIRE(c && keys_dev, "NULL argument");
     REQUIRE((coeffs_dev && bytes_dev) || pixels == 0, "NULL argument");
     CK(cudaSetDevice(c->device));
-    CK(ptm::launch_quantise(coeffs_dev, pixels, keys_dev, bytes_dev, sb_dev, false, c->sm_count, c->stream));
+    CK(ptm::launch_quantise(coeffs_dev, pixels, ptm::KeySource{keys_dev, nullptr, 0, 0}, bytes_dev, sb_dev, false,
+                            c->sm_count, c->stream));
     return 0;
 }
 
@@ -311,7 +298,109 @@ int ptmb_quantise_consume(ptmb_ctx_t *c, float *coeffs_dev, size_t pixels, const
     REQUIRE(c && keys_dev, "NULL argument");
     REQUIRE((coeffs_dev && bytes_dev) || pixels == 0, "NULL argument");
     CK(cudaSetDevice(c->device));
-    CK(ptm::launch_quantise(coeffs_dev, pixels, keys_dev, bytes_dev, sb_dev, true, c->sm_count, c->stream));
+    CK(ptm::launch_quantise(coeffs_dev, pixels, ptm::KeySource{keys_dev, nullptr, 0, 0}, bytes_dev, sb_dev, true,
+                            c->sm_count, c->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Whole device-resident LRGB encode of one slab in two launches: K1 hands the merged keys to the
+// mailbox of every rank from its last block (no keys-init, no separate exchange kernels), K2
+// picks them up in its prologue.
+// ---------------------------------------------------------------------------
+int ptmb_encode_lrgb_dev(ptmb_ctx_t *c, ptmb_xchg_t *x, const void *stack_dev, int sample_type, size_t image_stride,
+                         size_t pixels, float *coeffs_dev, uint8_t *rgb_dev, uint8_t *coef_bytes_dev,
+                         ptmb_scale_bias_t *sb_dev) {
+    ptm::FitArgs a;
+    if (make_fit_args(c, stack_dev, image_stride, pixels, a))
+        return 1;
+    REQUIRE(sample_type == PTMB_U8 || sample_type == PTMB_U16, "LRGB fit takes uint8 or uint16 stacks");
+    REQUIRE(coeffs_dev && rgb_dev && coef_bytes_dev, "output pointer is NULL");
+    REQUIRE(image_stride >= pixels * 3 * sample_size(sample_type), "image_stride smaller than one image");
+    REQUIRE(!x || x->device == c->device, "exchange belongs to another device");
+    CK(cudaSetDevice(c->device));
+    a.coeffs = coeffs_dev;
+    a.rgb = rgb_dev;
+    a.keys = c->keys_dev;   // kept at the initial extrema between encodes (reset by the hand-off)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (c->probe_next + 1 < c->probe_events.size()) {
+        ev0 = c->probe_events[c->probe_next];
+        ev1 = c->probe_events[c->probe_next + 1];
+        c->probe_next += 2;
+    }
+    if (ev0)
+        CK(cudaEventRecord(ev0, c->stream));
+
+    // fused form: one streaming launch covers the whole slab
+    ptm::KeySource src{};
+    size_t done = 0;
+    if (sample_type == PTMB_U8 && pixels > 0) {
+        a.handoff.ticket = c->ticket_dev;
+        a.handoff.world = x ? x->world : 1;
+        a.handoff.rank = x ? x->rank : 0;
+        a.handoff.epoch = x ? x->epoch + 1 : c->epoch + 1;
+        for (int r = 0; r < a.handoff.world; ++r)
+            a.handoff.mailbox[r] = x ? x->mailbox[r] : c->mailbox_dev;
+        // the hand-off may only ride on a launch that covers every pixel of the slab
+        const size_t rem = pixels % 1024;
+        const bool whole = rem % 16 == 0;
+        if (whole)
+            CK(ptm::launch_fit_lrgb_tma(a, c->sm_count, c->stream, &done));
+        if (done == pixels) {
+            if (x)
+                ++x->epoch;
+            else
+                ++c->epoch;
+            src.mailbox = x ? x->local : c->mailbox_dev;
+            src.world = a.handoff.world;
+            src.epoch = a.handoff.epoch;
+        } else {
+            REQUIRE(done == 0, "internal: partial streaming launch with a hand-off");
+        }
+    }
+    if (!src.mailbox) {
+        // general form: any layout / sample type, keys merged by separate kernels
+        a.handoff = ptm::KeyHandoff{};
+        CK(ptm::launch_fit_lrgb(a, sample_type, c->sm_count, c->stream));
+        if (x && ptmb_xchg_allreduce_max(c, x, c->keys_dev))
+            return 1;
+        src.keys = c->keys_dev;
+    }
+    if (ev1)
+        CK(cudaEventRecord(ev1, c->stream));
+    CK(ptm::launch_quantise(coeffs_dev, pixels, src, coef_bytes_dev, sb_dev, false, c->sm_count, c->stream));
+    if (!src.mailbox)
+        CK(ptm::launch_keys_init(c->keys_dev, c->stream));   // leave the context keys reset, as the hand-off does
+    return 0;
+}
+
+// Timing probes: the next `pairs` calls of ptmb_encode_lrgb_dev record a CUDA event before and after
+// their fit stage on the context's stream; ptmb_probe_read returns the elapsed milliseconds.
+int ptmb_probe_arm(ptmb_ctx_t *c, unsigned pairs) {
+    REQUIRE(c, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    for (cudaEvent_t ev : c->probe_events)
+        cudaEventDestroy(ev);
+    c->probe_events.clear();
+    c->probe_next = 0;
+    for (unsigned i = 0; i < 2 * pairs; ++i) {
+        cudaEvent_t ev;
+        CK(cudaEventCreate(&ev));
+        c->probe_events.push_back(ev);
+    }
+    return 0;
+}
+
+int ptmb_probe_read(ptmb_ctx_t *c, float *ms_out, unsigned pairs, unsigned *recorded) {
+    REQUIRE(c && ms_out && recorded, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    unsigned n = (unsigned) (c->probe_next / 2);
+    if (n > pairs)
+        n = pairs;
+    for (unsigned i = 0; i < n; ++i)
+        CK(cudaEventElapsedTime(&ms_out[i], c->probe_events[2 * i], c->probe_events[2 * i + 1]));
+    *recorded = n;
     return 0;
 }
 
@@ -560,7 +649,7 @@ int ptmb_encode_host_finish(ptmb_ctx_t *c, const int32_t *keys_dev, uint8_t *con
     const size_t pixels = s.pixels, plane_floats = pixels * PTMB_COEFFICIENTS;
     const uint8_t *rgb_dev = s.bytes + pixels * PTMB_COEFFICIENTS * s.planes;
     for (int b = s.planes - 1; b >= 0; --b)   // last-written plane first: it is the one still in L2
-        CK(ptm::launch_quantise(s.coeffs + b * plane_floats, pixels, keys,
+        CK(ptm::launch_quantise(s.coeffs + b * plane_floats, pixels, ptm::KeySource{keys, nullptr, 0, 0},
                                 s.bytes + (size_t) b * pixels * PTMB_COEFFICIENTS, b == 0 ? c->sb_dev : nullptr,
                                 coeffs_host == nullptr, c->sm_count, c->stream));
     for (int b = 0; b < s.planes; ++b)

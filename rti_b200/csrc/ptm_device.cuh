@@ -123,6 +123,82 @@ struct Extrema {
     }
 };
 
+// Called by every thread of every block right after Extrema::flush when a hand-off is set up.
+// The block that takes the last ticket owns the merged keys: it swaps them out (resetting them
+// for the next launch), stores them into slot [parity][rank] of every rank's mailbox, fences
+// system-wide and then raises the flags.  Peer mailboxes are plain P2P pointers over NVLink.
+template <typename Handoff, typename Layout>
+__device__ __forceinline__ void keys_handoff(const Handoff &h, int *keys, int max_ranks, int slot_ints) {
+    __shared__ int last_s;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        last_s = (atomicAdd(h.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last_s)
+        return;
+    __threadfence();
+    const int parity = h.epoch & 1;
+    if (threadIdx.x < 2 * PTM_NCOEF) {
+        const int v = atomicExch(&keys[threadIdx.x], float_to_key(-FLT_MAX));
+        for (int r = 0; r < h.world; ++r) {
+            int *slots = h.mailbox[r] + Layout::slots_off / sizeof(int);
+            slots[(parity * max_ranks + h.rank) * slot_ints + threadIdx.x] = v;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < h.world) {
+        volatile int *flags = h.mailbox[threadIdx.x] + Layout::flags_off / sizeof(int);
+        __threadfence_system();
+        flags[parity * max_ranks + h.rank] = (int) h.epoch;
+    }
+    if (threadIdx.x == 0)
+        *h.ticket = 0;
+}
+
+// K2 prologue: the 12 merged keys into shared memory, from plain keys or from the local mailbox
+// (one lane per rank polls its flag, bounded by a timeout that is reported in the mailbox status).
+template <typename Source, typename Layout>
+__device__ __forceinline__ void keys_fetch(const Source &src, int *keys_sh, int max_ranks, int slot_ints) {
+    __shared__ int ok_s;
+    if (src.mailbox == nullptr) {
+        if (threadIdx.x < 2 * PTM_NCOEF)
+            keys_sh[threadIdx.x] = src.keys[threadIdx.x];
+        __syncthreads();
+        return;
+    }
+    const int parity = src.epoch & 1;
+    volatile int *flags = src.mailbox + Layout::flags_off / sizeof(int);
+    if (threadIdx.x == 0)
+        ok_s = 1;
+    __syncthreads();
+    if (threadIdx.x < src.world) {
+        unsigned long long t0, t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (flags[parity * max_ranks + threadIdx.x] != (int) src.epoch) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > 5000000000ull) {
+                ok_s = 0;
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < 2 * PTM_NCOEF) {
+        const volatile int *slots = src.mailbox + Layout::slots_off / sizeof(int);
+        int m = slots[(parity * max_ranks + 0) * slot_ints + threadIdx.x];
+        for (int r = 1; r < src.world; ++r)
+            m = max(m, slots[(parity * max_ranks + r) * slot_ints + threadIdx.x]);
+        keys_sh[threadIdx.x] = m;
+    }
+    if (threadIdx.x == 0 && !ok_s)
+        src.mailbox[Layout::status_off / sizeof(int)] = 1;
+    __syncthreads();
+}
+
 // The LRGB colour + normalise step for one pixel (rti-builder/ptm-encoder.c:331-348).
 // (ya, cba, cra) are the truncated integer averages of rti-builder/ptmlib.c:794-796.
 __device__ __forceinline__ void lrgb_finish(unsigned ya, unsigned cba, unsigned cra, float *c,

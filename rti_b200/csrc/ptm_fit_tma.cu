@@ -232,6 +232,8 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
         }
     }
     ext.flush(a.keys, keys_s);
+    if (a.handoff.ticket)
+        keys_handoff<KeyHandoff, XchgLayout>(a.handoff, a.keys, kMaxRanks, kSlotInts);
 }
 
 template <int L, int S, int kDebug = 0>

@@ -1,0 +1,56 @@
+// Internal: context structures shared by the API translation units.
+#pragma once
+
+#include <vector>
+
+#include "../../include/ptm_b200.h"
+#include "ptm_kernels.h"
+
+struct EncodeScratch {
+    void *stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    float *coeffs = nullptr;
+    size_t coeff_floats = 0;
+    uint8_t *bytes = nullptr;  // planes * pixels * 6 (+ pixels * 3 for LRGB)
+    size_t out_bytes = 0;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    size_t pixels = 0;
+    int planes = 0;
+    bool valid = false;
+};
+
+struct ptmb_ctx {
+    EncodeScratch enc;
+    // key hand-off between K1 and K2 of the fused device encode
+    unsigned *ticket_dev = nullptr;          // last-block ticket counter (0 between launches)
+    int *mailbox_dev = nullptr;              // local mailbox used when no peer exchange is attached
+    unsigned epoch = 0;                      // epoch of the local mailbox
+    // optional timing probes around K1 (ptmb_probe_*)
+    std::vector<cudaEvent_t> probe_events;
+    size_t probe_next = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    std::vector<float> M_host;
+    float *M_dev = nullptr;
+    unsigned n_lights = 0;
+    unsigned magic = 0;
+    int *keys_dev = nullptr;                 // scratch for the host-buffer entry points
+    ptmb_scale_bias_t *sb_dev = nullptr;
+    std::vector<float> light_host;
+    float *light_dev = nullptr;
+    size_t light_cap = 0;
+    int32_t *lq_dev = nullptr;
+    size_t lq_cap = 0;
+};
+
+
+struct ptmb_xchg {
+    int device = 0;
+    int rank = 0, world = 1;
+    int *local = nullptr;
+    int *mailbox[ptm::kMaxRanks] = {};
+    bool opened[ptm::kMaxRanks] = {};
+    unsigned epoch = 0;
+};

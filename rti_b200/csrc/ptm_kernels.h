@@ -9,6 +9,34 @@ namespace ptm {
 
 constexpr int kFitThreads = 256;
 
+// Mailbox used to hand the extrema keys from the fit to the quantiser, on one GPU or across
+// GPUs (ptm_xchg.cu): slots[2][kMaxRanks][16] ints, flags[2][kMaxRanks] ints, status[4] ints.
+constexpr int kMaxRanks = 16;
+constexpr int kSlotInts = 16;  // 12 keys, padded to 64 bytes
+struct XchgLayout {
+    static constexpr size_t slots_off = 0;
+    static constexpr size_t flags_off = 2 * kMaxRanks * kSlotInts * sizeof(int);
+    static constexpr size_t status_off = flags_off + 2 * kMaxRanks * sizeof(int);
+    static constexpr size_t bytes = status_off + 4 * sizeof(int);
+};
+
+// What the LAST block of a fit launch does with the merged keys: deliver them to the mailbox of
+// every rank (its own included) under `epoch`, and reset keys + ticket for the next launch.
+struct KeyHandoff {
+    unsigned *ticket;           // device counter, 0 between launches; nullptr = no hand-off
+    int *mailbox[kMaxRanks];
+    int world, rank;
+    unsigned epoch;
+};
+
+// Where K2 takes the extrema from: plain keys, or the local mailbox (waits for all ranks' flags).
+struct KeySource {
+    const int *keys;
+    int *mailbox;               // nullptr = use keys
+    int world;
+    unsigned epoch;
+};
+
 struct FitArgs {
     const uint8_t *stack;   // [n_lights][pixels][3] samples, device
     size_t image_stride;    // bytes between two lights' images
@@ -20,6 +48,7 @@ struct FitArgs {
     size_t plane_stride;    // floats between RGB coefficient planes
     uint8_t *rgb;           // [pixels][3] (LRGB only)
     int *keys;              // [12]
+    KeyHandoff handoff;     // optional (ticket == nullptr: none)
 };
 
 struct RelightArgs {
@@ -44,7 +73,7 @@ cudaError_t launch_chroma_avg(const uint8_t *stack, size_t image_stride, size_t 
 cudaError_t launch_lrgb_colour_normalise(uint8_t *ycc, float *coeffs, size_t pixels, int sm_count,
                                          cudaStream_t st);
 cudaError_t launch_minmax(const float *coeffs, size_t pixels, int *keys, int sm_count, cudaStream_t st);
-cudaError_t launch_quantise(const float *coeffs, size_t pixels, const int *keys, uint8_t *bytes, void *sb,
+cudaError_t launch_quantise(const float *coeffs, size_t pixels, const KeySource &src, uint8_t *bytes, void *sb,
                             bool consume, int sm_count, cudaStream_t st);
 cudaError_t launch_relight(const RelightArgs &a, bool lrgb, int sm_count, cudaStream_t st);
 cudaError_t launch_div255_selftest(unsigned long long first, unsigned long long count,

@@ -20,9 +20,11 @@ constexpr int kQuantUnroll = 4;
 template <bool kConsume>
 __global__ void __launch_bounds__(kQuantThreads)
 quantise_kernel(const float *__restrict__ coeffs, size_t n_float4, size_t tail_first, size_t n_floats,
-                const int *__restrict__ keys, uint8_t *__restrict__ bytes, void *sb_out) {
+                KeySource ksrc, uint8_t *__restrict__ bytes, void *sb_out) {
     __shared__ float inv_s[PTM_NCOEF];
     __shared__ float bias_s[PTM_NCOEF];
+    __shared__ int keys[2 * PTM_NCOEF];
+    keys_fetch<KeySource, XchgLayout>(ksrc, keys, kMaxRanks, kSlotInts);
     if (threadIdx.x < PTM_NCOEF) {
         float scale, inv;
         int bias;
@@ -92,10 +94,12 @@ quantise_kernel(const float *__restrict__ coeffs, size_t n_float4, size_t tail_f
 
 // Everything through the scalar path: used when pointers are not 16 / 4 byte aligned.
 __global__ void __launch_bounds__(kQuantThreads)
-quantise_scalar_kernel(const float *__restrict__ coeffs, size_t n_floats, const int *__restrict__ keys,
+quantise_scalar_kernel(const float *__restrict__ coeffs, size_t n_floats, KeySource ksrc,
                        uint8_t *__restrict__ bytes, void *sb_out) {
     __shared__ float inv_s[PTM_NCOEF];
     __shared__ float bias_s[PTM_NCOEF];
+    __shared__ int keys[2 * PTM_NCOEF];
+    keys_fetch<KeySource, XchgLayout>(ksrc, keys, kMaxRanks, kSlotInts);
     if (threadIdx.x < PTM_NCOEF) {
         float scale, inv;
         int bias;
@@ -115,7 +119,7 @@ quantise_scalar_kernel(const float *__restrict__ coeffs, size_t n_floats, const 
     }
 }
 
-cudaError_t launch_quantise(const float *coeffs, size_t pixels, const int *keys, uint8_t *bytes, void *sb,
+cudaError_t launch_quantise(const float *coeffs, size_t pixels, const KeySource &keys, uint8_t *bytes, void *sb,
                             bool consume, int sm_count, cudaStream_t st) {
     const size_t n_floats = pixels * PTM_NCOEF;
     const bool aligned = ((uintptr_t) coeffs % 16 == 0) && ((uintptr_t) bytes % 4 == 0);

@@ -22,20 +22,10 @@
 
 #include "../../include/ptm_b200.h"
 #include "ptm_device.cuh"
+#include "ptm_internal.h"
 #include "ptm_kernels.h"
 
 namespace ptm {
-
-constexpr int kMaxRanks = 16;
-constexpr int kSlotInts = 16;  // 12 keys, padded to 64 bytes
-
-struct XchgLayout {
-    // one mailbox per GPU: slots[2][kMaxRanks][16] ints, flags[2][kMaxRanks] ints, status[4] ints
-    static constexpr size_t slots_off = 0;
-    static constexpr size_t flags_off = 2 * kMaxRanks * kSlotInts * sizeof(int);
-    static constexpr size_t status_off = flags_off + 2 * kMaxRanks * sizeof(int);
-    static constexpr size_t bytes = status_off + 4 * sizeof(int);
-};
 
 struct XchgPeers {
     int *mailbox[kMaxRanks];
@@ -92,15 +82,6 @@ __global__ void xchg_gather_kernel(int *mailbox, int world, unsigned epoch, int 
 
 }  // namespace ptm
 
-struct ptmb_xchg {
-    int device = 0;
-    int rank = 0, world = 1;
-    int *local = nullptr;
-    ptm::XchgPeers peers{};
-    bool opened[ptm::kMaxRanks] = {};
-    unsigned epoch = 0;
-};
-
 extern "C" int ptmb_internal_fail(const char *what, const char *detail);
 extern "C" int ptmb_internal_device(const ptmb_ctx_t *c);
 extern "C" void *ptmb_internal_stream(const ptmb_ctx_t *c);
@@ -135,7 +116,7 @@ int ptmb_xchg_create(ptmb_ctx_t *c, int rank, int world, ptmb_xchg_t **out, void
         return ptmb_internal_fail("ptmb_xchg_create", cudaGetErrorString(e));
     }
     memcpy(handle_out, &h, sizeof(h));
-    x->peers.mailbox[rank] = x->local;
+    x->mailbox[rank] = x->local;
     *out = x;
     return 0;
 }
@@ -151,7 +132,7 @@ int ptmb_xchg_connect(ptmb_xchg_t *x, const void *handles) {
         memcpy(&h, (const char *) handles + (size_t) r * sizeof(h), sizeof(h));
         void *p = nullptr;
         CKX(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-        x->peers.mailbox[r] = (int *) p;
+        x->mailbox[r] = (int *) p;
         x->opened[r] = true;
     }
     return 0;
@@ -165,7 +146,10 @@ int ptmb_xchg_allreduce_max(ptmb_ctx_t *c, ptmb_xchg_t *x, int32_t *keys_dev) {
     CKX(cudaSetDevice(x->device));
     cudaStream_t st = (cudaStream_t) ptmb_internal_stream(c);
     const unsigned epoch = ++x->epoch;
-    ptm::xchg_publish_kernel<<<1, ptm::kMaxRanks * ptm::kSlotInts, 0, st>>>(x->peers, x->world, x->rank, epoch, keys_dev);
+    ptm::XchgPeers peers{};
+    for (int r = 0; r < x->world; ++r)
+        peers.mailbox[r] = x->mailbox[r];
+    ptm::xchg_publish_kernel<<<1, ptm::kMaxRanks * ptm::kSlotInts, 0, st>>>(peers, x->world, x->rank, epoch, keys_dev);
     CKX(cudaGetLastError());
     ptm::xchg_gather_kernel<<<1, 32, 0, st>>>(x->local, x->world, epoch, keys_dev, 5000000000ull);
     CKX(cudaGetLastError());
@@ -191,7 +175,7 @@ void ptmb_xchg_destroy(ptmb_xchg_t *x) {
     cudaDeviceSynchronize();
     for (int r = 0; r < x->world; ++r)
         if (x->opened[r])
-            cudaIpcCloseMemHandle(x->peers.mailbox[r]);
+            cudaIpcCloseMemHandle(x->mailbox[r]);
     cudaFree(x->local);
     delete x;
 }

@@ -116,6 +116,22 @@ class Context:
         fn = self._lib.ptmb_quantise_consume if consume else self._lib.ptmb_quantise
         _lib.check(fn(self._h, _ptr(coeffs), pixels, _ptr(keys), _ptr(out_bytes), _ptr(scale_bias)))
 
+    def encode_lrgb_dev(self, stack, image_stride, pixels, coeffs, rgb, coef_bytes, scale_bias=None,
+                        xchg=None, sample_type=U8):
+        """Whole device-resident LRGB encode of one slab (K1 -> key hand-off -> K2, two launches)."""
+        _lib.check(self._lib.ptmb_encode_lrgb_dev(self._h, None if xchg is None else xchg._h, _ptr(stack),
+                                                  sample_type, image_stride, pixels, _ptr(coeffs), _ptr(rgb),
+                                                  _ptr(coef_bytes), _ptr(scale_bias)))
+
+    def probe_arm(self, pairs):
+        _lib.check(self._lib.ptmb_probe_arm(self._h, pairs))
+
+    def probe_read(self, pairs):
+        out = (C.c_float * pairs)()
+        n = C.c_uint(0)
+        _lib.check(self._lib.ptmb_probe_read(self._h, out, pairs, C.byref(n)))
+        return [out[i] for i in range(n.value)]
+
     def relight_lrgb(self, coef, rgb, width, height, scale, bias, uv, out):
         scale = np.ascontiguousarray(scale, dtype=np.float32)
         bias = np.ascontiguousarray(bias, dtype=np.int32)

@@ -96,8 +96,8 @@ class PtmEncoder:
         import torch.distributed as dist
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.exchange_kind = "none" if not multi else ("p2p" if self.xchg is not None else "nccl")
-        # keys-init, K1, K2 per plane (+ publish and gather kernels of the peer exchange)
-        self.launches_per_encode = 2 + self.planes + (2 if self.xchg is not None else 0)
+        # fused LRGB encode: K1 + K2; otherwise keys-init, K1, K2 per plane
+        self.launches_per_encode = 2 if (self.planes == 1 and self.exchange_kind in ("none", "p2p")) else 2 + self.planes
 
     def _use_current_stream(self):
         self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
@@ -128,6 +128,14 @@ class PtmEncoder:
                               self.sb if b == 0 else None, consume=not self.keep_coeffs)
 
     def encode(self, stack):
+        """fit -> exchange -> quantise.  LRGB with the peer (or no) exchange goes through the fused
+        two-launch entry (ptmb_encode_lrgb_dev); self.keys is not updated on that path."""
+        if self.planes == 1 and self.exchange_kind in ("none", "p2p"):
+            assert stack.is_cuda and stack.is_contiguous() and stack.shape[0] == self.n_lights
+            st = {torch.uint8: U8, torch.uint16: U16}[stack.dtype]
+            self.ctx.encode_lrgb_dev(stack, self.pixels * 3 * stack.element_size(), self.pixels, self.coeffs,
+                                     self.rgb, self.coef_bytes, self.sb, xchg=self.xchg, sample_type=st)
+            return
         self.fit(stack)
         self.exchange()
         self.quantise()

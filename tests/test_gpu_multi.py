@@ -42,8 +42,15 @@ def _worker(rank, world, port, H, W, ret):
             enc.encode(slab)
         torch.cuda.synchronize()
         status = enc.xchg.status() if enc.xchg is not None else 0
-        out[kind] = (enc.exchange_kind, status, enc.keys.cpu().numpy(), enc.coef_bytes[0].cpu().numpy(),
+        # the fused path leaves no keys; scale / bias (derived from the merged keys) stand in
+        out[kind] = (enc.exchange_kind, status, enc.sb.cpu().numpy(), enc.coef_bytes[0].cpu().numpy(),
                      enc.rgb.cpu().numpy())
+        # stepwise calls through the same exchange still work after fused ones
+        enc.fit(slab)
+        enc.exchange()
+        enc.quantise()
+        torch.cuda.synchronize()
+        assert np.array_equal(enc.sb.cpu().numpy(), out[kind][2])
     ret[rank] = (r0, r1, out)
     dist.destroy_process_group()
 
@@ -70,7 +77,7 @@ def test_two_gpu_slabs_equal_single_gpu():
     for kind in ("p2p", "nccl"):
         for r in range(world):
             assert ret[r][2][kind][1] == 0
-            np.testing.assert_array_equal(ret[r][2][kind][2], full.keys.cpu().numpy())
+            np.testing.assert_array_equal(ret[r][2][kind][2], full.sb.cpu().numpy())
         coef = np.concatenate([ret[r][2][kind][3] for r in range(world)])
         rgb = np.concatenate([ret[r][2][kind][4] for r in range(world)])
         np.testing.assert_array_equal(coef, full.coef_bytes[0].cpu().numpy())

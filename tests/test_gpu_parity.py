@@ -334,9 +334,19 @@ def test_full_size_properties(ctx, oracle, dome1, M60):
     stack = torch.empty((n, H, W, 3), dtype=torch.uint8, device="cuda")
     ctx.synth(0x5EED0001, 0, U8, 0, P, light_q14(dome1), stack, P * 3)
     enc = PtmEncoder(W, H, M60, planes=1)
-    enc.encode(stack)
+    enc.fit(stack)
+    enc.exchange()
+    enc.quantise()
     torch.cuda.synchronize()
     scale, bias = enc.scale_bias()
+    # (0) the fused two-launch entry gives the same bytes, scale and bias, call after call
+    fused = PtmEncoder(W, H, M60, planes=1)
+    for _ in range(3):
+        fused.encode(stack)
+    torch.cuda.synchronize()
+    assert torch.equal(fused.coef_bytes, enc.coef_bytes) and torch.equal(fused.rgb, enc.rgb)
+    assert torch.equal(fused.sb, enc.sb)
+    del fused
     # (1) extrema agree with an independent pass over the floats
     keys2 = torch.empty(12, dtype=torch.int32, device="cuda")
     ctx.keys_init(keys2)
