@@ -171,7 +171,7 @@ int ptmb_host_unregister(const void *host) {
 
 int ptmb_set_matrix(ptmb_ctx_t *c, const float *M, unsigned n_lights) {
     REQUIRE(c && M, "NULL argument");
-    REQUIRE(n_lights >= 1 && n_lights <= 4096, "n_lights must be in 1..4096");
+    REQUIRE(n_lights >= 1 && n_lights <= 2048, "n_lights must be in 1..2048 (the pinv table lives in shared memory)");
     CK(cudaSetDevice(c->device));
     if (n_lights != c->n_lights || !c->M_dev) {
         CK(cudaStreamSynchronize(c->stream));

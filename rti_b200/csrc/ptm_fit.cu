@@ -407,25 +407,33 @@ cudaError_t launch_fit_lrgb(const FitArgs &a, int sample_type, int sm_count, cud
 cudaError_t launch_fit_rgb(const FitArgs &a, int sample_type, int sm_count, cudaStream_t st) {
     if (a.pixels == 0)
         return cudaSuccess;
-    const bool vec_ok = sample_type == 0 && ((uintptr_t) a.stack % 4 == 0) && (a.image_stride % 4 == 0) &&
-                        ((uintptr_t) a.coeffs % 16 == 0) && (a.plane_stride % 4 == 0);
+    const size_t gen_smem = (size_t) a.n_lights * PTM_NCOEF * sizeof(float);
+    if (sample_type == 1) {   // 16-bit stacks: generic kernel (not tuned in this round)
+        const unsigned grid = grid_for(a.pixels * 3, kFitThreads, sm_count, 8);
+        fit_rgb_generic_kernel<uint16_t><<<grid, kFitThreads, gen_smem, st>>>(a, 0);
+        return cudaGetLastError();
+    }
+    if (sample_type != 0)
+        return cudaErrorInvalidValue;
+    // 1) streaming kernel over whole tiles (+ a 16-pixel-granular partial tile)
     size_t done = 0;
-    if (vec_ok && a.pixels >= 4) {
+    cudaError_t e = launch_fit_rgb_tma(a, sm_count, st, &done);
+    if (e != cudaSuccess)
+        return e;
+    // 2) 4-pixel groups through the register kernel for word-aligned layouts
+    const bool vec_ok = ((uintptr_t) a.stack % 4 == 0) && (a.image_stride % 4 == 0) &&
+                        ((uintptr_t) a.coeffs % 16 == 0) && (a.plane_stride % 4 == 0);
+    if (done == 0 && vec_ok && a.pixels >= 4) {
         const size_t groups = a.pixels / 4;
         const unsigned grid = grid_for(groups, kFitThreads, sm_count, 2);
         const size_t smem = (size_t) a.n_lights * 2 * sizeof(float4);
         fit_rgb_u8_kernel<<<grid, kFitThreads, smem, st>>>(a);
         done = groups * 4;
     }
+    // 3) the rest, one (pixel, channel) per thread
     if (done < a.pixels) {
         const unsigned grid = grid_for((a.pixels - done) * 3, kFitThreads, sm_count, 8);
-        const size_t gen_smem = (size_t) a.n_lights * PTM_NCOEF * sizeof(float);
-        if (sample_type == 0)
-            fit_rgb_generic_kernel<uint8_t><<<grid, kFitThreads, gen_smem, st>>>(a, done);
-        else if (sample_type == 1)
-            fit_rgb_generic_kernel<uint16_t><<<grid, kFitThreads, gen_smem, st>>>(a, done);
-        else
-            return cudaErrorInvalidValue;
+        fit_rgb_generic_kernel<uint8_t><<<grid, kFitThreads, gen_smem, st>>>(a, done);
     }
     return cudaGetLastError();
 }

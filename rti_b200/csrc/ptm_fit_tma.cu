@@ -272,6 +272,223 @@ static cudaError_t launch_variant(const FitArgs &a, size_t n_tiles, unsigned tai
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// RGB formats: the same ring, but every byte of the stack is a sample of its own fit
+// (rti-builder/ptm-encoder.c:272-284): a lane keeps 4 pixels x 3 channels x 6 = 72 accumulators,
+// as 36 packed pairs updated with FFMA2 (fma.rn.f32x2, the sample broadcast to both halves and a
+// coefficient pair of the pinv column as the other operand).  Output: three planes [pixels][6],
+// only plane 0 feeds the extrema (rti-builder/ptmlib.c:831).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ffma2_bcast(float s, unsigned long long m, unsigned long long c) {
+    unsigned long long ss, d;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ss) : "f"(s));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(ss), "l"(m), "l"(c));
+    return d;
+}
+
+__device__ __forceinline__ void consume_light_rgb(const uint32_t *s32, const float4 *m,
+                                                  unsigned long long (&acc)[12][3]) {
+    const unsigned w[3] = {s32[0], s32[1], s32[2]};
+    const float4 ma = m[0], mb = m[1];
+    unsigned long long m01, m23, m45;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(m01) : "f"(ma.x), "f"(ma.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(m23) : "f"(ma.z), "f"(ma.w));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(m45) : "f"(mb.x), "f"(mb.y));
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {   // byte j of the 12 = pixel j / 3, channel j % 3
+        const float v = byte_to_float(w[j >> 2], 0x7650u + (j & 3));
+        acc[j][0] = ffma2_bcast(v, m01, acc[j][0]);
+        acc[j][1] = ffma2_bcast(v, m23, acc[j][1]);
+        acc[j][2] = ffma2_bcast(v, m45, acc[j][2]);
+    }
+}
+
+constexpr int kRgbWarps = 7;                             // 7 consumer warps + 1 producer = 256 threads:
+constexpr int kRgbThreads = kRgbWarps * 32 + 32;         //   two CTAs per SM get 128 registers per thread
+constexpr int kRgbTilePx = kRgbWarps * 128;              // 896 pixels
+constexpr int kRgbTileBytes = kRgbTilePx * 3;            // 2688 bytes per light (a multiple of 16)
+
+template <int L, int S>
+struct RgbSmem {
+    static constexpr size_t stage_bytes = (size_t) L * kRgbTileBytes;
+    static constexpr size_t bars = (size_t) S * stage_bytes;
+    static constexpr size_t staging = bars + 2 * S * sizeof(uint64_t);
+    static constexpr size_t matrix = staging + (size_t) kRgbWarps * kWarpStageBytes;
+    static constexpr size_t total(unsigned n_lights) { return matrix + (size_t) n_lights * 32; }
+};
+
+template <int L, int S, bool kFull>
+__global__ void __launch_bounds__(kRgbThreads, 2)
+fit_rgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
+    using Smem = RgbSmem<L, S>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ int keys_s[2 * PTM_NCOEF];
+    uint8_t *ring = smem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Smem::bars);
+    uint64_t *empty = full + S;
+    float4 *m_s = reinterpret_cast<float4 *>(smem + Smem::matrix);
+
+    const unsigned n = a.n_lights;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        const float *M = a.M;
+        m_s[2 * i] = make_float4(M[i], M[n + i], M[2 * n + i], M[3 * n + i]);
+        m_s[2 * i + 1] = make_float4(M[4 * n + i], M[5 * n + i], 0.f, 0.f);
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kRgbWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned n_chunks = (n + L - 1) / L;
+    Extrema ext;
+    ext.init();
+
+    if (warp == kRgbWarps) {
+        const uint64_t policy = l2_policy_evict_first();
+        unsigned s = 0, ph = 0;
+        for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint8_t *src = a.stack + (size_t) tile * kRgbTileBytes + (size_t) lane * a.image_stride;
+            const unsigned bytes = (tail_px && tile + 1 == n_tiles) ? tail_px * 3 : (unsigned) kRgbTileBytes;
+            for (unsigned c = 0; c < n_chunks; ++c) {
+                const unsigned l0 = c * L;
+                const unsigned cnt = kFull ? (unsigned) L : min((unsigned) L, n - l0);
+                if (lane == 0) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full[s], cnt * bytes);
+                }
+                __syncwarp();
+                if (lane < cnt)
+                    bulk_g2s(ring + (size_t) s * Smem::stage_bytes + (size_t) lane * kRgbTileBytes,
+                             src + (size_t) l0 * a.image_stride, bytes, &full[s], policy);
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+    } else {
+        const unsigned t = threadIdx.x;
+        unsigned s = 0, ph = 0;
+        for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            unsigned long long acc[12][3];
+#pragma unroll
+            for (int j = 0; j < 12; ++j)
+                acc[j][0] = acc[j][1] = acc[j][2] = 0ull;   // two +0.0f
+
+            for (unsigned c = 0; c < n_chunks; ++c) {
+                mbar_wait(&full[s], ph);
+                const uint32_t *buf = reinterpret_cast<const uint32_t *>(ring + (size_t) s * Smem::stage_bytes) + 3 * t;
+                const unsigned l0 = c * L;
+                const unsigned cnt = kFull ? (unsigned) L : min((unsigned) L, n - l0);
+                if (cnt == L) {
+#pragma unroll
+                    for (unsigned l = 0; l < L; ++l)
+                        consume_light_rgb(buf + l * (kRgbTileBytes / 4), m_s + 2 * (l0 + l), acc);
+                } else {
+                    for (unsigned l = 0; l < cnt; ++l)
+                        consume_light_rgb(buf + l * (kRgbTileBytes / 4), m_s + 2 * (l0 + l), acc);
+                }
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(&empty[s]);
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+
+            const unsigned tile_px = (tail_px && tile + 1 == n_tiles) ? tail_px : (unsigned) kRgbTilePx;
+            const unsigned valid = min(128u, tile_px > warp * 128 ? tile_px - warp * 128 : 0u);
+            const size_t wpx = (size_t) tile * kRgbTilePx + (size_t) warp * 128;
+            uint8_t *stg = smem + Smem::staging + (size_t) warp * kWarpStageBytes;
+            if (4 * t < tile_px) {
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    float c0[PTM_NCOEF];
+#pragma unroll
+                    for (int h = 0; h < 3; ++h) {
+                        c0[2 * h] = __uint_as_float((unsigned) (acc[p * 3][h] & 0xFFFFFFFFull));
+                        c0[2 * h + 1] = __uint_as_float((unsigned) (acc[p * 3][h] >> 32));
+                    }
+                    ext.add(c0);
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                // lane's 4 pixels of this channel: 24 floats = 12 packed pairs, laid out like the plane
+                unsigned long long *row = reinterpret_cast<unsigned long long *>(stg) + lane * 12;
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int h = 0; h < 3; ++h)
+                        row[p * 3 + h] = acc[p * 3 + ch][h];
+                __syncwarp();
+                float4 *dst = reinterpret_cast<float4 *>(a.coeffs + (size_t) ch * a.plane_stride + wpx * PTM_NCOEF);
+                const float4 *src = reinterpret_cast<const float4 *>(stg);
+#pragma unroll
+                for (int r = 0; r < 6; ++r)
+                    if (lane + 32 * r < valid * 6 / 4)
+                        __stcg(dst + lane + 32 * r, src[lane + 32 * r]);
+                __syncwarp();
+            }
+        }
+    }
+    ext.flush(a.keys, keys_s);
+}
+
+template <int L, int S>
+static cudaError_t launch_rgb_variant(const FitArgs &a, size_t n_tiles, unsigned tail_px, int sm_count,
+                                      cudaStream_t st) {
+    using Smem = RgbSmem<L, S>;
+    static int per_sm_cache[64][2];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return e;
+    if (dev < 0 || dev >= 64)
+        return cudaErrorInvalidDevice;
+    const bool full = a.n_lights % L == 0;
+    auto kern = full ? fit_rgb_u8_tma_kernel<L, S, true> : fit_rgb_u8_tma_kernel<L, S, false>;
+    if (per_sm_cache[dev][full] == 0) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Smem::total(257));
+        if (e != cudaSuccess)
+            return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kRgbThreads, Smem::total(257));
+        if (e != cudaSuccess)
+            return e;
+        if (nb < 1)
+            return cudaErrorLaunchOutOfResources;
+        per_sm_cache[dev][full] = nb;
+    }
+    size_t grid = (size_t) sm_count * per_sm_cache[dev][full];
+    if (grid > n_tiles)
+        grid = n_tiles;
+    kern<<<(unsigned) grid, kRgbThreads, Smem::total(a.n_lights), st>>>(a, (unsigned) n_tiles, tail_px);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fit_rgb_tma(const FitArgs &a, int sm_count, cudaStream_t st, size_t *done) {
+    *done = 0;
+    const bool ok = a.n_lights <= 2048 && ((uintptr_t) a.stack % 16 == 0) && (a.image_stride % 16 == 0) &&
+                    ((uintptr_t) a.coeffs % 16 == 0) && (a.plane_stride % 4 == 0);
+    const size_t full_tiles = a.pixels / kRgbTilePx;
+    const unsigned rem = (unsigned) (a.pixels % kRgbTilePx);
+    const unsigned tail_px = (rem % 16 == 0) ? rem : 0;
+    const size_t n_tiles = full_tiles + (tail_px ? 1 : 0);
+    if (!ok || n_tiles == 0 || n_tiles > 0xFFFFFFFFull || a.n_lights > 257)
+        return cudaSuccess;
+    cudaError_t e = launch_rgb_variant<6, 4>(a, n_tiles, tail_px, sm_count, st);
+    if (e == cudaSuccess)
+        *done = full_tiles * kRgbTilePx + tail_px;
+    return e;
+}
+
 // Launches the streaming kernel over the whole 1024-pixel tiles of the slab and returns how many
 // pixels it covered through *done (0 if the layout does not allow bulk copies).
 cudaError_t launch_fit_lrgb_tma(const FitArgs &a, int sm_count, cudaStream_t st, size_t *done) {
