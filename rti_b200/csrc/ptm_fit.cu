@@ -373,9 +373,15 @@ cudaError_t launch_fit_lrgb(const FitArgs &a, int sample_type, int sm_count, cud
     if (sample_type != 0 && sample_type != 1)
         return cudaErrorInvalidValue;
     const size_t gen_smem = (size_t) a.n_lights * PTM_NCOEF * sizeof(float);
-    if (sample_type == 1) {   // 16-bit stacks: generic kernel only (not tuned in this round)
-        const unsigned grid = grid_for(a.pixels, kFitThreads, sm_count, 8);
-        fit_lrgb_generic_kernel<uint16_t><<<grid, kFitThreads, gen_smem, st>>>(a, 0);
+    if (sample_type == 1) {   // 16-bit stacks: streaming kernel over the tiles, generic kernel for the rest
+        size_t done16 = 0;
+        cudaError_t e16 = launch_fit_u16_tma(a, false, sm_count, st, &done16);
+        if (e16 != cudaSuccess)
+            return e16;
+        if (done16 < a.pixels) {
+            const unsigned grid = grid_for(a.pixels - done16, kFitThreads, sm_count, 8);
+            fit_lrgb_generic_kernel<uint16_t><<<grid, kFitThreads, gen_smem, st>>>(a, done16);
+        }
         return cudaGetLastError();
     }
     // 1) whole 1024-pixel tiles through the streaming (bulk copy) kernel when the layout allows it
@@ -408,9 +414,15 @@ cudaError_t launch_fit_rgb(const FitArgs &a, int sample_type, int sm_count, cuda
     if (a.pixels == 0)
         return cudaSuccess;
     const size_t gen_smem = (size_t) a.n_lights * PTM_NCOEF * sizeof(float);
-    if (sample_type == 1) {   // 16-bit stacks: generic kernel (not tuned in this round)
-        const unsigned grid = grid_for(a.pixels * 3, kFitThreads, sm_count, 8);
-        fit_rgb_generic_kernel<uint16_t><<<grid, kFitThreads, gen_smem, st>>>(a, 0);
+    if (sample_type == 1) {   // 16-bit stacks: streaming kernel over the tiles, generic kernel for the rest
+        size_t done16 = 0;
+        cudaError_t e16 = launch_fit_u16_tma(a, true, sm_count, st, &done16);
+        if (e16 != cudaSuccess)
+            return e16;
+        if (done16 < a.pixels) {
+            const unsigned grid = grid_for((a.pixels - done16) * 3, kFitThreads, sm_count, 8);
+            fit_rgb_generic_kernel<uint16_t><<<grid, kFitThreads, gen_smem, st>>>(a, done16);
+        }
         return cudaGetLastError();
     }
     if (sample_type != 0)

@@ -64,6 +64,7 @@ struct RelightArgs {
 cudaError_t launch_keys_init(int *keys, cudaStream_t st);
 cudaError_t launch_fit_lrgb(const FitArgs &a, int sample_type, int sm_count, cudaStream_t st);
 cudaError_t launch_fit_lrgb_tma(const FitArgs &a, int sm_count, cudaStream_t st, size_t *done);
+cudaError_t launch_fit_u16_tma(const FitArgs &a, bool rgb, int sm_count, cudaStream_t st, size_t *done);
 cudaError_t launch_fit_rgb_tma(const FitArgs &a, int sm_count, cudaStream_t st, size_t *done);
 cudaError_t launch_fit_rgb(const FitArgs &a, int sample_type, int sm_count, cudaStream_t st);
 cudaError_t launch_fit_channel(const void *samples, int sample_type, size_t pixel_stride, size_t image_stride,

@@ -458,7 +458,13 @@ def test_sixteen_bit_stacks(ctx, oracle):
     from rti_b200.device import U16
     L = lights.dome100_lights()
     M = oracle.pinv(L)
-    W, H = 40, 26
+    _sixteen_bit_case(ctx, oracle, L, M, 40, 26)      # 1040 px: one streaming tile + a 144 px partial tile
+    _sixteen_bit_case(ctx, oracle, L, M, 37, 29)      # 1073 px: tile + generic remainder
+    _sixteen_bit_case(ctx, oracle, L, M, 24, 10)      # 240 px: partial tile only
+
+
+def _sixteen_bit_case(ctx, oracle, L, M, W, H):
+    from rti_b200.device import U16
     P = W * H
     ctx.set_matrix(M)
     keys = torch.empty(12, dtype=torch.int32, device="cuda")
