@@ -169,23 +169,30 @@ __device__ __forceinline__ void keys_fetch(const Source &src, int *keys_sh, int 
         return;
     }
     const int parity = src.epoch & 1;
-    volatile int *flags = src.mailbox + Layout::flags_off / sizeof(int);
+    const int *flags = src.mailbox + Layout::flags_off / sizeof(int);
     if (threadIdx.x == 0)
         ok_s = 1;
     __syncthreads();
     if (threadIdx.x < src.world) {
-        unsigned long long t0, t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        while (flags[parity * max_ranks + threadIdx.x] != (int) src.epoch) {
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            if (t - t0 > 5000000000ull) {
-                ok_s = 0;
-                break;
-            }
-            __nanosleep(64);
+        // acquire load at system scope pairs with the publisher's fence + flag store; the block
+        // barrier below extends the ordering to the lanes that read the slots (no fence per CTA)
+        const int *f = flags + parity * max_ranks + threadIdx.x;
+        unsigned long long t0 = 0, t;
+        int v;
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (v != (int) src.epoch) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            do {
+                __nanosleep(64);
+                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t - t0 > 5000000000ull) {
+                    ok_s = 0;
+                    break;
+                }
+            } while (v != (int) src.epoch);
         }
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x < 2 * PTM_NCOEF) {
         const volatile int *slots = src.mailbox + Layout::slots_off / sizeof(int);
