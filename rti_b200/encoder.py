@@ -103,12 +103,14 @@ class PtmEncoder:
         self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
     def fit(self, stack):
-        """K1 on the slab; leaves float coefficients (+ RGB) and local extrema keys."""
-        assert stack.is_cuda and stack.is_contiguous()
+        """K1 on the slab; leaves float coefficients (+ RGB) and local extrema keys.  `stack` is
+        [n_lights, rows, width, 3], contiguous per light; lights may be strided (a row range of a
+        larger stack), which is how a slab of a resident image is passed without a copy."""
+        assert stack.is_cuda and stack.dim() == 4 and stack[0].is_contiguous()
         n = stack.shape[0]
-        assert n == self.n_lights and stack.numel() == n * self.pixels * 3
+        assert n == self.n_lights and stack[0].numel() == self.pixels * 3
         st = {torch.uint8: U8, torch.uint16: U16}[stack.dtype]
-        image_stride = self.pixels * 3 * stack.element_size()
+        image_stride = (stack.stride(0) if n > 1 else self.pixels * 3) * stack.element_size()
         self.ctx.keys_init(self.keys)
         if self.planes == 1:
             self.ctx.fit_lrgb(stack, image_stride, self.pixels, self.coeffs, self.rgb, self.keys, st)

@@ -501,3 +501,93 @@ def _sixteen_bit_case(ctx, oracle, L, M, W, H):
     norm = 256.0 / np.floor(y16[..., 0].astype(np.float64).sum(0) / 100)
     bound = np.einsum("kn,nhw->hwk", np.abs(M).astype(np.float64), y16[..., 0].astype(np.float64)) * norm[..., None]
     assert (np.abs(got - want["coeffs"]) / bound).max() <= 1e-5
+
+
+def test_full_size_sixteen_bit_100_lights(ctx, oracle):
+    """BASELINE.json configs[3] at full size: 50 MP (8688 x 5755), 100 lights, uint16 (30 GB stack).
+    Size-independent checks: the RGB-format encode of two uneven slabs with merged keys equals the
+    whole-image encode byte for byte, and sampled rows agree with the oracle (ptm_fit_poly_uint
+    semantics) -- for the LRGB extension too."""
+    from rti_b200 import lights
+    from rti_b200.device import U16, light_q14
+    from rti_b200.encoder import PtmEncoder
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs about 60 GB of free HBM")
+    W, H, n = 8688, 5755, 100
+    P = W * H
+    L = lights.dome100_lights()
+    M = oracle.pinv(L)
+    stack = torch.empty((n, H, W, 3), dtype=torch.uint16, device="cuda")
+    ctx.synth(0x5EED0004, 1, U16, 0, P, light_q14(L), stack, P * 6)
+    enc = PtmEncoder(W, H, M, planes=3)
+    enc.encode(stack)
+    torch.cuda.synchronize()
+    scale, bias = enc.scale_bias()
+    rows = [0, 2871, H - 1]
+    sub = np.stack([stack[:, r].view(torch.int16).cpu().numpy().view(np.uint16) for r in rows], axis=1)
+    for ch in range(3):
+        want = oracle.fit_u32(sub.astype(np.uint32), M, ch)
+        got = enc.coeffs[ch].reshape(H, W, 6)[rows].cpu().numpy()
+        assert coeff_error(got, want, M, sub[..., ch]) <= 1e-5
+        inv = (np.float32(1.0) / scale).astype(np.float32)
+        q = (want * inv).astype(np.float32) + bias.astype(np.float32)
+        want_b = np.where(q > 255, 255, np.where(q < 0, 0, q)).astype(np.uint8)
+        assert_bytes_close(enc.coef_bytes[ch].reshape(H, W, 6)[rows].cpu().numpy(), want_b, "50 MP u16 rows, plane %d" % ch)
+    whole = enc.coef_bytes.clone()
+    keys_whole = enc.keys.clone()
+    del enc
+    # slab invariance (the multi-GPU claim) with uneven slabs
+    cut = 2001
+    parts = []
+    for r0, r1 in ((0, cut), (cut, H)):
+        e = PtmEncoder(W, r1 - r0, M, planes=3)
+        e.fit(stack[:, r0:r1])        # a row range of a contiguous stack is NOT contiguous per light ...
+        parts.append((r0, r1, e))
+    merged = torch.stack([e.keys for _, _, e in parts]).max(0).values
+    assert torch.equal(merged, keys_whole)
+    for r0, r1, e in parts:
+        e.keys.copy_(merged)
+        e.quantise()
+        for ch in range(3):
+            assert torch.equal(e.coef_bytes[ch], whole[ch][r0 * W:r1 * W])
+
+
+def test_full_size_relight_sweep(ctx, oracle, dome1, M60):
+    """BASELINE.json configs[4] at full size: a 24 MP LRGB PTM relit for 360 directions in one call
+    (26 GB of rasters).  Sampled rows of sampled directions equal the oracle exactly, and every
+    raster equals the same direction relit on its own (batching does not change a byte)."""
+    from rti_b200.device import U8, light_q14
+    from rti_b200.encoder import PtmEncoder
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs about 40 GB of free HBM")
+    W, H = 6000, 4000
+    P = W * H
+    stack = torch.empty((60, H, W, 3), dtype=torch.uint8, device="cuda")
+    ctx.synth(0x5EED0001, 0, U8, 0, P, light_q14(dome1), stack, P * 3)
+    enc = PtmEncoder(W, H, M60)
+    enc.encode(stack)
+    torch.cuda.synchronize()
+    del stack
+    scale, bias = enc.scale_bias()
+    scale = oracle.header_roundtrip(scale)
+    th = np.deg2rad(np.arange(360, dtype=np.float64))
+    uv = np.stack([0.7 * np.cos(th), 0.7 * np.sin(th)], 1).astype(np.float32)
+    out = torch.empty((360, H, W, 3), dtype=torch.uint8, device="cuda")
+    ctx.relight_lrgb(enc.coef_bytes[0], enc.rgb, W, H, scale, bias, uv, out)
+    torch.cuda.synchronize()
+    # stored rows for output rows y: H-1-y
+    ys = [0, 1777, H - 1]
+    coef = enc.coef_bytes[0].reshape(H, W, 6)
+    rgb = enc.rgb.reshape(H, W, 3)
+    for d in (0, 97, 359):
+        for y in ys:
+            c_row = coef[H - 1 - y].cpu().numpy()[None]
+            r_row = rgb[H - 1 - y].cpu().numpy()[None]
+            want = oracle.relight_lrgb(c_row, r_row, scale, bias, float(uv[d, 0]), float(uv[d, 1]))
+            np.testing.assert_array_equal(out[d, y].cpu().numpy(), want[0])
+    single = torch.empty((1, H, W, 3), dtype=torch.uint8, device="cuda")
+    for d in (5, 200):
+        ctx.relight_lrgb(enc.coef_bytes[0], enc.rgb, W, H, scale, bias, uv[d:d + 1], single)
+        assert torch.equal(single[0], out[d])
