@@ -110,6 +110,25 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPU cores NVML reports as local to the GPU, so that the pinned host
+    buffers of the e2e leg are first-touched on the GPU's NUMA node (matters with one rank per GPU)."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def physical_gpu_index(local):
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     if vis:
@@ -197,6 +216,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        bind_to_gpu_numa_node(physical_gpu_index(local))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
 

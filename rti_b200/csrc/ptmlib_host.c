@@ -58,8 +58,18 @@ static void gpu_die (const char *what) {
 
 static ptmb_ctx_t *gpu (void) {
     if (!g_ctx) {
+        /* PTM_B200_DEVICE selects the GPU (default 0).  A one-shot command line pays for CUDA
+         * start-up on every run, and the driver initialises every visible GPU (about 1 s on an
+         * 8-GPU box): unless the user already restricted visibility, expose only the chosen one. */
         const char *dev = getenv ("PTM_B200_DEVICE");
-        if (ptmb_create (dev ? atoi (dev) : 0, NULL, &g_ctx))
+        int ordinal = dev ? atoi (dev) : 0;
+        if (!getenv ("CUDA_VISIBLE_DEVICES")) {
+            char buf[16];
+            snprintf (buf, sizeof (buf), "%d", ordinal);
+            setenv ("CUDA_VISIBLE_DEVICES", buf, 1);
+            ordinal = 0;
+        }
+        if (ptmb_create (ordinal, NULL, &g_ctx))
             gpu_die ("ptmb_create");
     }
     return g_ctx;

@@ -1,14 +1,15 @@
 #!/usr/bin/env python
-"""Small end-to-end pass for compute-sanitizer (memcheck): every kernel family once, odd and
-even sizes, so out-of-bounds accesses in tile / tail handling show up.
-    compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
+"""Small end-to-end pass over every kernel family, odd and even sizes, so that out-of-bounds
+accesses in tile / tail handling show up under compute-sanitizer memcheck where that tool is
+available (it is closed on this pool; the pass is also a quick all-kernel smoke on its own):
+    python tests/tools/all_kernels_smoke.py"""
 import os
 import sys
 
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import oracle as O  # noqa: E402  (tools/ is test tooling)
 from rti_b200 import lights  # noqa: E402
