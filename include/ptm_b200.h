@@ -199,6 +199,25 @@ int ptmb_encode_lrgb_dev (ptmb_ctx_t *ctx, ptmb_xchg_t *xchg, const void *stack_
 int ptmb_probe_arm (ptmb_ctx_t *ctx, unsigned pairs);
 int ptmb_probe_read (ptmb_ctx_t *ctx, float *ms_out, unsigned pairs, unsigned *recorded);
 
+/* JPEG in and out through nvJPEG (the codec the reference takes from libjpeg:
+ * rti-builder/ptm-encoder.c:181-190,248-264, rti-builder/ptmlib.c:371-412,473-520,565-627).
+ *   ptmb_jpeg_info    dimensions and component count (1 = grayscale, else 3) of a JPEG in memory.
+ *   ptmb_jpeg_decode  -> interleaved [height][width][components].  want_rgb = 0 delivers YCbCr the
+ *                     way libjpeg does with out_color_space = JCS_YCbCr (no colour conversion, chroma
+ *                     upsampled with libjpeg's triangle filter); 1 delivers RGB.  `out` is host memory,
+ *                     or device memory when out_is_device (e.g. one light's image inside the stack, so
+ *                     that only the compressed bytes cross PCIe); flip stores the bottom row first like
+ *                     rti-builder/ptm-encoder.c:252-256.
+ *   ptmb_jpeg_encode  interleaved host image (1 = gray, 3 = RGB or YCbCr) -> malloc'd JPEG, baseline,
+ *                     4:2:0 for colour, given quality.
+ * The inverse DCT is nvJPEG's, so decoded samples may differ from libjpeg's by an LSB. */
+int ptmb_jpeg_info (ptmb_ctx_t *ctx, const uint8_t *data, size_t len, unsigned *width, unsigned *height,
+                    unsigned *components);
+int ptmb_jpeg_decode (ptmb_ctx_t *ctx, const uint8_t *data, size_t len, int want_rgb, int flip, void *out,
+                      int out_is_device);
+int ptmb_jpeg_encode (ptmb_ctx_t *ctx, const uint8_t *pixels_host, unsigned width, unsigned height,
+                      unsigned components, int input_is_ycbcr, int quality, uint8_t **jpeg_out, size_t *jpeg_len);
+
 /* Host-pointer forms of the individual steps, for callers that keep the reference's own
  * call sequence through ptmlib.h (each streams its operands through device slabs):
  *   ptmb_fit_channel_host            ptm_fit_poly_jsample / _uint   rti-builder/ptmlib.c:692-760

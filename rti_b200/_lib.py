@@ -66,6 +66,9 @@ _SIGNATURES = {
     "ptmb_encode_lrgb_dev": ([_vp, _vp, _vp, _int, _sz, _sz, _vp, _vp, _vp, _vp], _int),
     "ptmb_probe_arm": ([_vp, C.c_uint], _int),
     "ptmb_probe_read": ([_vp, _vp, C.c_uint, C.POINTER(C.c_uint)], _int),
+    "ptmb_jpeg_info": ([_vp, _vp, _sz, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)], _int),
+    "ptmb_jpeg_decode": ([_vp, _vp, _sz, _int, _int, _vp, _int], _int),
+    "ptmb_jpeg_encode": ([_vp, _vp, C.c_uint, C.c_uint, C.c_uint, _int, _int, C.POINTER(_vp), C.POINTER(_sz)], _int),
     "ptmb_fit_channel_host": ([_vp, _vp, _int, _sz, _sz, _sz, C.c_uint, _vp, _vp], _int),
     "ptmb_chroma_avg_host": ([_vp, _vp, _sz, C.c_uint, _vp], _int),
     "ptmb_lrgb_colour_normalise_host": ([_vp, _vp, _vp, _sz], _int),

@@ -109,7 +109,9 @@ int main (int argc, char *argv[]) {
 
     size_t cap = 64, n = 0;
     decoder_t **decoders = malloc (cap * sizeof (*decoders));
-    ptm_image_dims_t dims0 = { 0, 0, 0 };
+    ptm_image_dims_t *all_dims = malloc (cap * sizeof (*all_dims));
+    ptm_image_dims_t dims0;
+    memset (&dims0, 0, sizeof (dims0));
 
     char *line = NULL;
     size_t len = 0;
@@ -145,10 +147,12 @@ int main (int argc, char *argv[]) {
             d->dinfo.output_width = dims.width;
             d->dinfo.output_height = dims.height;
             d->dinfo.output_components = (int) dims.components;
+            all_dims[n] = dims;
             decoders[n++] = d;
             if (n >= cap) {
                 cap *= 2;
                 decoders = realloc (decoders, cap * sizeof (*decoders));
+                all_dims = realloc (all_dims, cap * sizeof (*all_dims));
             }
         } else {
             free (name);
@@ -195,9 +199,11 @@ int main (int argc, char *argv[]) {
         unsigned char **rows = calloc (info.height, sizeof (*rows));
         for (size_t y = 0; y < info.height; ++y)
             rows[y] = buffer + i * info.decoder_stride + (info.height - y - 1) * info.row_stride;
-        ptm_image_dims_t d = { (unsigned int) info.width, (unsigned int) info.height, dims0.components };
-        if (ptm_codec_read_rows (decoders[i]->fp, &d, rows, (unsigned int) info.height))
+        /* YCbCr for the LUM / LRGB formats, RGB for the RGB formats (ref :186-188) */
+        if (ptm_codec_read_rows (decoders[i]->fp, &all_dims[i], rows, (unsigned int) info.height,
+                                 header->format->color_components == 0))
             failed = 1;
+        ptm_codec_release (&all_dims[i]);
         fclose (decoders[i]->fp);
         free (rows);
     }
@@ -240,6 +246,7 @@ int main (int argc, char *argv[]) {
         free (decoders[i]);
     }
     free (decoders);
+    free (all_dims);
     free (header);
     return 0;
 }

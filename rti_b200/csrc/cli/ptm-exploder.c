@@ -72,7 +72,6 @@ int main (int argc, char *argv[]) {
         ext = filename + strlen (argv[3]);
 
     const size_t pixels = header->dimen[0] * header->dimen[1];
-    const ptm_image_dims_t dims = { (unsigned int) header->dimen[0], (unsigned int) header->dimen[1], 3 };
     /* batches bound host memory: about 1 GiB of rasters at a time */
     size_t batch = pixels ? (1u << 30) / (pixels * 3) : 1;
     if (batch < 1)
@@ -90,7 +89,8 @@ int main (int argc, char *argv[]) {
                 fprintf (stderr, "can't open %s\n", filename);
                 return 1;
             }
-            if (ptm_codec_write (out, rasters + d * pixels * 3, &dims))
+            if (ptm_codec_write (out, rasters + d * pixels * 3, (unsigned int) header->dimen[0],
+                                 (unsigned int) header->dimen[1], 3, 0, header->compression_param[0]))
                 fprintf (stderr, "cannot write image\n");
             fclose (out);
         }

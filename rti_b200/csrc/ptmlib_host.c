@@ -75,6 +75,11 @@ static ptmb_ctx_t *gpu (void) {
     return g_ctx;
 }
 
+/* for ptm_codec.c and the command lines (not part of ptmlib.h) */
+ptmb_ctx_t *ptm_internal_gpu (void) {
+    return gpu ();
+}
+
 static int sample_bytes (const ptm_header_t *h, int n_block) {
     /* ref :286-290 -- colour blocks are always sized for 3 components */
     return n_block < h->format->ptm_blocks ? PTM_COEFFICIENTS : RGB_COEFFICIENTS;
@@ -282,14 +287,14 @@ static void read_stream_blocks (FILE *fp, const ptm_header_t *h, ptm_block_t *bl
         unsigned char *packed = malloc (h->compressed_size[i] ? h->compressed_size[i] : 1);
         if (fread (packed, 1, h->compressed_size[i], fp) != h->compressed_size[i])
             fprintf (stderr, "short read in PTM stream %d\n", i);
-        ptm_image_dims_t dims;
-        if (ptm_codec_decode_mem (packed, h->compressed_size[i], &dims, &planes[i])) {
+        unsigned int pw = 0, ph = 0, pc = 0;
+        if (ptm_codec_decode_mem (packed, h->compressed_size[i], &pw, &ph, &pc, &planes[i])) {
             fprintf (stderr, "cannot decode PTM stream %d\n", i);
             exit (1);
         }
-        assert (dims.width == width);
-        assert (dims.height == height);
-        assert (dims.components == 1);
+        assert (pw == width);
+        assert (ph == height);
+        assert (pc == 1);
         free (packed);
         if (h->side_info_sizes[i] > 0) {
             side[i] = malloc (h->side_info_sizes[i]);
@@ -339,9 +344,9 @@ static void write_stream_blocks (FILE *fp, ptm_header_t *h, ptm_block_t *blocks)
         JSAMPLE *plane = malloc (pixels ? pixels : 1);
         for (size_t p = 0; p < pixels; ++p)
             plane[p] = src[p * step];
-        ptm_image_dims_t dims = { (unsigned int) width, (unsigned int) height, 1 };
         size_t size = 0;
-        if (ptm_codec_encode_mem (plane, &dims, &streams[i], &size)) {
+        if (ptm_codec_encode_mem (plane, (unsigned int) width, (unsigned int) height, h->compression_param[0],
+                                  &streams[i], &size)) {
             fprintf (stderr, "cannot encode PTM stream %d\n", i);
             exit (1);
         }
@@ -520,8 +525,9 @@ void ptm_write_jpeg (FILE *fp, const ptm_header_t *h, ptm_block_t *blocks, float
     const size_t pixels = h->dimen[0] * h->dimen[1];
     JSAMPLE *raster = malloc (pixels > 0 ? pixels * 3 : 1);
     ptm_relight (h, blocks, u, v, raster);
-    ptm_image_dims_t dims = { (unsigned int) h->dimen[0], (unsigned int) h->dimen[1], 3 };
-    if (ptm_codec_write (fp, raster, &dims))
+    /* quality from the header, RGB colour space (ref :575-577; LUM would be YCbCr) */
+    if (ptm_codec_write (fp, raster, (unsigned int) h->dimen[0], (unsigned int) h->dimen[1], 3, 0,
+                         h->compression_param[0]))
         fprintf (stderr, "cannot write image\n");
     free (raster);
 }

@@ -147,6 +147,34 @@ class Context:
                                               scale.ctypes.data, bias.ctypes.data, uv.ctypes.data, uv.shape[0],
                                               _ptr(out)))
 
+    def jpeg_info(self, data):
+        w, h, c = C.c_uint(0), C.c_uint(0), C.c_uint(0)
+        _lib.check(self._lib.ptmb_jpeg_info(self._h, data, len(data), C.byref(w), C.byref(h), C.byref(c)))
+        return w.value, h.value, c.value
+
+    def jpeg_decode(self, data, want_rgb=False, flip=False, out=None):
+        """JPEG bytes -> uint8 [h][w][c] (numpy), or into `out` (a CUDA tensor / device address)."""
+        w, h, c = self.jpeg_info(data)
+        if out is None:
+            res = np.empty((h, w, c), np.uint8)
+            _lib.check(self._lib.ptmb_jpeg_decode(self._h, data, len(data), int(want_rgb), int(flip),
+                                                  res.ctypes.data, 0))
+            return res
+        _lib.check(self._lib.ptmb_jpeg_decode(self._h, data, len(data), int(want_rgb), int(flip), _ptr(out), 1))
+        return out
+
+    def jpeg_encode(self, image, ycbcr=False, quality=90):
+        """uint8 [h][w] or [h][w][3] (numpy) -> JPEG bytes."""
+        img = np.ascontiguousarray(image, dtype=np.uint8)
+        h, w = img.shape[:2]
+        comps = 1 if img.ndim == 2 else img.shape[2]
+        p, n = C.c_void_p(), C.c_size_t(0)
+        _lib.check(self._lib.ptmb_jpeg_encode(self._h, img.ctypes.data, w, h, comps, int(ycbcr), quality,
+                                              C.byref(p), C.byref(n)))
+        data = C.string_at(p, n.value)
+        C.CDLL(None).free(p)
+        return data
+
     def selftest_div255(self, first_bits=0, count=1 << 32):
         """Mismatch count of K3's division / CLIP shortcuts against IEEE / the reference."""
         n = C.c_uint64(0)

@@ -34,8 +34,10 @@ def write_inputs(oracle, d, stack_stored, lights):
     return lp
 
 
-def run(cmd, **kw):
-    return subprocess.run(cmd, capture_output=True, env=dict(os.environ, OPENBLAS_NUM_THREADS="1"), **kw)
+def run(cmd, codec="raw", **kw):
+    # PTM_IMAGE_CODEC=raw: the lossless container on both sides, so that files compare byte for byte
+    return subprocess.run(cmd, capture_output=True,
+                          env=dict(os.environ, OPENBLAS_NUM_THREADS="1", PTM_IMAGE_CODEC=codec), **kw)
 
 
 @pytest.mark.parametrize("fmt,mode", [("PTM_FORMAT_LRGB", 0), ("PTM_FORMAT_RGB", 1),
@@ -123,3 +125,56 @@ def test_cli_errors_match_reference(tmp_path):
     assert r.returncode == 1 and b"not a PTM file" in r.stderr
     r = run([os.path.join(BIN, "ptm-exploder"), "a", "b"])
     assert r.returncode == 1 and b"Usage:" in r.stderr
+
+
+def test_real_jpeg_files_end_to_end(oracle, dome1, tmp_path):
+    """Real JPEG inputs and outputs through nvJPEG: Pillow writes the 60 input photographs (4:2:0),
+    ptm-encoder reads them, ptm-decoder writes a JPEG that Pillow reads back.  Compared with the
+    oracle pipeline run on Pillow's own (libjpeg) YCbCr decode of the same files -- the two JPEG
+    decoders differ by an LSB here and there, so this checks agreement, not identity."""
+    import io
+    from PIL import Image
+    d = str(tmp_path)
+    W, H = 96, 64
+    stack = oracle.synth_stack(0xC13, 0, W, H, dome1)          # YCbCr triplets, stored row order
+    names, decoded = [], []
+    for i in range(60):
+        ycc_top_first = stack[i, ::-1]
+        im = Image.fromarray(np.ascontiguousarray(ycc_top_first), mode="YCbCr")
+        name = "img%03d.jpg" % i
+        im.save(os.path.join(d, name), format="JPEG", quality=95, subsampling=2)
+        back = Image.open(os.path.join(d, name))
+        back.draft("YCbCr", back.size)
+        decoded.append(np.asarray(back)[::-1])                   # what libjpeg would put into the stack
+        names.append(name)
+    lp = os.path.join(d, "sample.lp")
+    with open(lp, "w") as fp:
+        fp.write("60\n")
+        for name, (u, v, w) in zip(names, dome1):
+            fp.write("%s %.9g %.9g %.9g\n" % (name, u, v, w))
+    ptm = os.path.join(d, "out.ptm")
+    r = run([os.path.join(BIN, "ptm-encoder"), "-f", "PTM_FORMAT_LRGB", "-o", ptm, lp], codec="jpeg")
+    assert r.returncode == 0, r.stderr.decode()
+    got = oracle.parse_ptm(open(ptm, "rb").read())
+    want = oracle.encode_lrgb(np.ascontiguousarray(np.stack(decoded)), oracle.pinv(dome1))
+    np.testing.assert_allclose(got["scale"], want["scale"], rtol=0.05)
+    rgb_diff = np.abs(got["blocks"][1].astype(int) - want["rgb"].astype(int))
+    assert rgb_diff.max() <= 3 and rgb_diff.mean() < 0.3
+    r = run([os.path.join(BIN, "ptm-decoder"), ptm, "0.2", "0.1"], codec="jpeg")
+    assert r.returncode == 0 and r.stdout[:2] == b"\xff\xd8", r.stderr.decode()
+    relit = np.asarray(Image.open(io.BytesIO(r.stdout)).convert("RGB")).astype(np.float64)
+    ref = oracle.relight_lrgb(want["coef"], want["rgb"], oracle.header_roundtrip(want["scale"]), want["bias"], 0.2, 0.1)
+    mse = ((relit - ref.astype(np.float64)) ** 2).mean()
+    psnr = 10 * np.log10(255.0 ** 2 / max(mse, 1e-9))
+    print("relit JPEG vs oracle raster: PSNR %.1f dB" % psnr)
+    assert psnr > 28
+    # the JPEG-compressed PTM format really holds JPEG streams now, and our decoder reads it back
+    ptmj = os.path.join(d, "outj.ptm")
+    r = run([os.path.join(BIN, "ptm-encoder"), "-f", "PTM_FORMAT_JPEG_LRGB", "-o", ptmj, lp], codec="jpeg")
+    assert r.returncode == 0 and b"\xff\xd8\xff" in open(ptmj, "rb").read()
+    assert os.path.getsize(ptmj) < os.path.getsize(ptm)
+    r2 = run([os.path.join(BIN, "ptm-decoder"), ptmj, "0.2", "0.1"], codec="raw")
+    assert r2.returncode == 0
+    relit2 = oracle.read_rawj(r2.stdout).astype(np.float64)
+    mse2 = ((relit2 - ref.astype(np.float64)) ** 2).mean()
+    assert 10 * np.log10(255.0 ** 2 / max(mse2, 1e-9)) > 24

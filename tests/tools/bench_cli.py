@@ -20,7 +20,7 @@ from rti_b200 import lights  # noqa: E402
 
 def timed(cmd, **kw):
     t0 = time.perf_counter()
-    r = subprocess.run(cmd, capture_output=True, env=dict(os.environ, OPENBLAS_NUM_THREADS="1"), **kw)
+    r = subprocess.run(cmd, capture_output=True, env=dict(os.environ, OPENBLAS_NUM_THREADS="1", PTM_IMAGE_CODEC="raw"), **kw)
     assert r.returncode == 0, r.stderr.decode()[-400:]
     return time.perf_counter() - t0, r
 
