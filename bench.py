@@ -336,7 +336,7 @@ def run_b200(args):
     out = {
         "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32 accumulate over u8 samples", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "24MP (%dx%d) x %d lights dome1.lp, LRGB uint8, row-sharded over %d GPU(s)"
                                % (W, H, N_LIGHTS, world),
                    "rows_per_gpu": rows, "l2": "inputs larger than L2 (%.0f MB stack per GPU, streamed once per step)"

@@ -208,6 +208,12 @@ void ptm_lrgb_finish (const ptm_image_info_t *info, ycbcr_coefficients_t *ycbcr_
 void ptm_encode_stack (ptm_header_t *ptm_header, const ptm_image_info_t *info, const JSAMPLE *buffer,
                        const float *M, ptm_block_t *blocks);
 
+/* The same from JPEG files held in memory: nvJPEG decodes every image straight into the stack on the
+ * GPU (only compressed bytes cross PCIe).  Returns 0 on success; non-zero means "use ptm_encode_stack". */
+int ptm_encode_jpeg_files (ptm_header_t *ptm_header, const ptm_image_info_t *info,
+                           const unsigned char *const *jpegs, const size_t *lens, const float *M,
+                           ptm_block_t *blocks);
+
 /* Relight without the codec: RGB raster [height][width][3] into `out`; the batch form takes
  * n_dirs (u, v) pairs and fills n_dirs rasters in one GPU pass (what ptm-exploder needs). */
 void ptm_relight (const ptm_header_t *ptm_header, ptm_block_t *blocks, float u, float v, JSAMPLE *out);

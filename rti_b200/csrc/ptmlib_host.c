@@ -499,6 +499,72 @@ void ptm_encode_stack (ptm_header_t *h, const ptm_image_info_t *info, const JSAM
     }
 }
 
+/* Encode straight from JPEG files: every image is decoded by nvJPEG INTO the device-resident stack
+ * (bottom row first, like rti-builder/ptm-encoder.c:252-256), so only the compressed bytes cross
+ * PCIe; then the fit / quantise kernels run on the stack and the blocks come back.  `jpegs[i]` /
+ * `lens[i]` are the n_decoders compressed files in memory.  Returns 0 on success, non-zero if the
+ * inputs are not usable this way (the caller then takes the host-buffer path). */
+int ptm_encode_jpeg_files (ptm_header_t *h, const ptm_image_info_t *info, const unsigned char *const *jpegs,
+                           const size_t *lens, const float *M, ptm_block_t *blocks) {
+    ptmb_ctx_t *ctx = gpu ();
+    const size_t pixels = info->pixels, n = info->n_decoders;
+    const int planes = h->format->ptm_blocks;
+    if (h->format->color_components == 2)
+        return 1;   /* LUM goes through the step-by-step path */
+    void *stack = NULL, *coeffs = NULL, *bytes = NULL, *sb = NULL, *keys = NULL;
+    /* image stride rounded up to 16 bytes keeps every light on the bulk-copy alignment */
+    const size_t stride = (pixels * 3 + 15) & ~(size_t) 15;
+    int rc = 1;
+    if (ptmb_malloc (ctx, stride * n, &stack) || ptmb_malloc (ctx, pixels * 24 * planes, &coeffs) ||
+        ptmb_malloc (ctx, pixels * 6 * planes + pixels * 3, &bytes) || ptmb_malloc (ctx, sizeof (ptmb_scale_bias_t), &sb) ||
+        ptmb_malloc (ctx, PTMB_KEYS * sizeof (int32_t), &keys))
+        goto done;
+    if (ptmb_set_matrix (ctx, M, (unsigned) n))
+        goto done;
+    for (size_t i = 0; i < n; ++i) {
+        unsigned w = 0, hgt = 0, c = 0;
+        if (ptmb_jpeg_info (ctx, jpegs[i], lens[i], &w, &hgt, &c) || w != info->width || hgt != info->height || c != 3)
+            goto done;
+        if (ptmb_jpeg_decode (ctx, jpegs[i], lens[i], h->format->color_components == 0, 1,
+                              (unsigned char *) stack + i * stride, 1))
+            goto done;
+    }
+    unsigned char *rgb_dev = (unsigned char *) bytes + pixels * 6 * planes;
+    if (planes == 1) {
+        if (ptmb_encode_lrgb_dev (ctx, NULL, stack, PTMB_U8, stride, pixels, coeffs, rgb_dev, bytes, sb))
+            goto done;
+    } else {
+        if (ptmb_keys_init (ctx, keys) || ptmb_fit_rgb (ctx, stack, PTMB_U8, stride, pixels, coeffs, pixels * 6, keys))
+            goto done;
+        for (int b = 0; b < planes; ++b)
+            if (ptmb_quantise (ctx, (float *) coeffs + (size_t) b * pixels * 6, pixels, keys,
+                               (unsigned char *) bytes + (size_t) b * pixels * 6, b == 0 ? sb : NULL))
+                goto done;
+    }
+    for (int b = 0; b < planes; ++b)
+        if (ptmb_download (ctx, blocks[b], (unsigned char *) bytes + (size_t) b * pixels * 6, pixels * 6))
+            goto done;
+    if (planes == 1 && ptmb_download (ctx, blocks[1], rgb_dev, pixels * 3))
+        goto done;
+    ptmb_scale_bias_t sbh;
+    if (ptmb_download (ctx, &sbh, sb, sizeof (sbh)))
+        goto done;
+    for (int i = 0; i < PTM_COEFFICIENTS; ++i) {
+        h->scale[i] = sbh.scale[i];
+        h->bias[i] = sbh.bias[i];
+    }
+    rc = 0;
+done:
+    if (rc)
+        fprintf (stderr, "ptmlib (B200): device JPEG path not used: %s\n", ptmb_last_error ());
+    ptmb_free (ctx, stack);
+    ptmb_free (ctx, coeffs);
+    ptmb_free (ctx, bytes);
+    ptmb_free (ctx, sb);
+    ptmb_free (ctx, keys);
+    return rc;
+}
+
 /* the pixel loop of ref :587-621, for a batch of light directions */
 void ptm_relight_batch (const ptm_header_t *h, ptm_block_t *blocks, const float *uv, unsigned int n_dirs,
                         JSAMPLE *out) {
