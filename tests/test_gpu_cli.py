@@ -178,3 +178,53 @@ def test_real_jpeg_files_end_to_end(oracle, dome1, tmp_path):
     relit2 = oracle.read_rawj(r2.stdout).astype(np.float64)
     mse2 = ((relit2 - ref.astype(np.float64)) ** 2).mean()
     assert 10 * np.log10(255.0 ** 2 / max(mse2, 1e-9)) > 24
+
+
+def have_dropin():
+    return all(os.path.exists(os.path.join(REF, "ptm-%s-dropin" % n)) for n in ("encoder", "decoder", "exploder"))
+
+
+@pytest.mark.parametrize("fmt,mode", [("PTM_FORMAT_LRGB", 0), ("PTM_FORMAT_RGB", 1), ("PTM_FORMAT_JPEG_LRGB", 0)])
+def test_reference_mains_linked_against_our_library(oracle, dome1, tmp_path, fmt, mode):
+    """The drop-in claim itself: the reference's UNMODIFIED ptm-encoder.c / ptm-decoder.c /
+    ptm-exploder.c, compiled against the reference's own ptmlib.h, but linked against OUR libptm.so
+    instead of ptmlib.o (oracle/Makefile, target dropin).  Every ptm_* call of those mains then runs on
+    the GPU; the output must match the all-reference build within the usual +-1 LSB and must be
+    IDENTICAL to our own command line (same kernels, same floats)."""
+    if not (have_ref() and have_dropin()):
+        pytest.skip("oracle/_ref drop-in mains not built")
+    d = str(tmp_path)
+    W, H = 80, 44
+    stack = oracle.synth_stack(0xD40, mode, W, H, dome1)
+    lp = write_inputs(oracle, d, stack, dome1)
+    outs = {}
+    for tag, exe in (("ref", os.path.join(REF, "ptm-encoder-ref")), ("dropin", os.path.join(REF, "ptm-encoder-dropin")),
+                     ("ours", os.path.join(BIN, "ptm-encoder"))):
+        path = os.path.join(d, tag + ".ptm")
+        r = run([exe, "-f", fmt, "-o", path, lp])
+        assert r.returncode == 0, (tag, r.stderr.decode())
+        outs[tag] = open(path, "rb").read()
+    assert outs["dropin"] == outs["ours"], "reference main on our library differs from our own main"
+    a = np.frombuffer(outs["dropin"], np.uint8)
+    b = np.frombuffer(outs["ref"], np.uint8)
+    assert a.size == b.size
+    nl = 6 if "JPEG" not in fmt else 14
+    ha, hb = outs["dropin"].split(b"\n", nl)[:nl], outs["ref"].split(b"\n", nl)[:nl]
+    assert ha[:4] == hb[:4] and ha[6:] == hb[6:]
+    if ha[4:6] == hb[4:6]:
+        diff = np.abs(a.astype(int) - b.astype(int))
+        assert diff.max() <= 1 and (diff != 0).mean() < 0.01
+    # decoder and exploder mains of the reference on our library: bit-identical rasters
+    ref_ptm = os.path.join(d, "ref.ptm")
+    ra = run([os.path.join(REF, "ptm-decoder-dropin"), ref_ptm, "0.4", "-0.3"])
+    rb = run([os.path.join(REF, "ptm-decoder-ref"), ref_ptm, "0.4", "-0.3"])
+    assert ra.returncode == 0 and rb.returncode == 0, ra.stderr.decode()
+    assert ra.stdout == rb.stdout
+    if fmt == "PTM_FORMAT_LRGB":
+        os.makedirs(os.path.join(d, "a"))
+        os.makedirs(os.path.join(d, "b"))
+        ra = run([os.path.join(REF, "ptm-exploder-dropin"), ref_ptm, lp, os.path.join(d, "a", "o.jpg")])
+        rb = run([os.path.join(REF, "ptm-exploder-ref"), ref_ptm, lp, os.path.join(d, "b", "o.jpg")])
+        assert ra.returncode == 0 and rb.returncode == 0
+        for f in sorted(os.listdir(os.path.join(d, "b")))[::7]:
+            assert open(os.path.join(d, "a", f), "rb").read() == open(os.path.join(d, "b", f), "rb").read(), f
