@@ -591,3 +591,50 @@ def test_full_size_relight_sweep(ctx, oracle, dome1, M60):
     for d in (5, 200):
         ctx.relight_lrgb(enc.coef_bytes[0], enc.rgb, W, H, scale, bias, uv[d:d + 1], single)
         assert torch.equal(single[0], out[d])
+
+
+def _ring_lights(n):
+    """n light directions on three rings (any n >= 6 gives a well conditioned design matrix)."""
+    th = np.arange(n) * (2 * np.pi / n) * 3.0
+    r = np.array([0.25, 0.55, 0.85])[np.arange(n) % 3]
+    u, v = r * np.cos(th), r * np.sin(th)
+    return np.stack([u, v, np.sqrt(1 - u * u - v * v)], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("n", [13, 100, 257, 300])
+def test_light_counts_that_do_not_fill_the_ring_stages(ctx, oracle, n):
+    """Light counts that are not a multiple of the ring's lights-per-stage (partial last stage),
+    the largest count of the 16-bit-lane byte sums (257) and one beyond it (generic kernels)."""
+    from rti_b200.device import U16
+    L = _ring_lights(n)
+    M = oracle.pinv(L)
+    W, H = 72, 33                                    # 2376 px: full tiles + a partial tile
+    P = W * H
+    stack = oracle.synth_stack(0x1000 + n, 0, W, H, L)
+    want = oracle.encode_lrgb(stack, M)
+    got = gpu_encode_lrgb(ctx, stack, M)
+    np.testing.assert_array_equal(got["rgb"], want["rgb"])
+    assert coeff_error(got["coeffs"], want["coeffs"], M, stack[..., 0], lrgb=True) <= 1e-5
+    # scale = (max - min) / 256 of float sums over n terms: the summation-order noise of the two
+    # extrema grows with n and is divided by a range that can be small
+    scale_tol = 3e-6 if n <= 100 else 3e-5
+    np.testing.assert_allclose(got["scale"], want["scale"], rtol=scale_tol)
+    if np.array_equal(got["bias"], want["bias"]):
+        assert_bytes_close(got["coef"], want["coef"], "LRGB bytes, %d lights" % n, 0.03)
+    # RGB format, same light set
+    st3 = oracle.synth_stack(0x2000 + n, 1, W, H, L)
+    w3 = oracle.encode_rgb(st3, M)
+    g3 = gpu_encode_rgb(ctx, st3, M)
+    for ch in range(3):
+        assert coeff_error(g3["coeffs"][ch], w3["coeffs"][ch], M, st3[..., ch]) <= 1e-5
+    np.testing.assert_allclose(g3["scale"], w3["scale"], rtol=scale_tol)
+    # 16-bit, same light set (stage size 4 there)
+    s16 = oracle.synth_stack(0x3000 + n, 1, W, H, L, dtype=np.uint16)
+    w16 = oracle.encode_rgb_u16(s16, M)
+    ctx.set_matrix(M)
+    coeffs = torch.empty((3, P, 6), dtype=torch.float32, device="cuda")
+    keys = torch.empty(12, dtype=torch.int32, device="cuda")
+    ctx.keys_init(keys)
+    ctx.fit_rgb(dev(s16.view(np.int16)).view(torch.uint16), P * 6, P, coeffs, P * 6, keys, U16)
+    for ch in range(3):
+        assert coeff_error(coeffs[ch].cpu().numpy().reshape(H, W, 6), w16["coeffs"][ch], M, s16[..., ch]) <= 1e-5
