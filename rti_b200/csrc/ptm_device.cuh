@@ -106,15 +106,12 @@ struct Extrema {
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < PTM_NCOEF; ++k) {
-            float a = -mn[k], b = mx[k];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                a = fmaxf(a, __shfl_xor_sync(0xFFFFFFFFu, a, off));
-                b = fmaxf(b, __shfl_xor_sync(0xFFFFFFFFu, b, off));
-            }
+            // integer max of the order-preserving keys == float max; one REDUX per value
+            const int a = __reduce_max_sync(0xFFFFFFFFu, float_to_key(-mn[k]));
+            const int b = __reduce_max_sync(0xFFFFFFFFu, float_to_key(mx[k]));
             if ((threadIdx.x & 31) == 0) {
-                atomicMax(&smem_keys[k], float_to_key(a));
-                atomicMax(&smem_keys[PTM_NCOEF + k], float_to_key(b));
+                atomicMax(&smem_keys[k], a);
+                atomicMax(&smem_keys[PTM_NCOEF + k], b);
             }
         }
         __syncthreads();
@@ -146,6 +143,8 @@ __device__ __forceinline__ void keys_handoff(const Handoff &h, int *keys, int ma
             slots[(parity * max_ranks + h.rank) * slot_ints + threadIdx.x] = v;
         }
     }
+    if (threadIdx.x == 0)
+        *h.ticket = 0;   // before the flags: once they are up the next fit may be on its way
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x < h.world) {
@@ -153,8 +152,6 @@ __device__ __forceinline__ void keys_handoff(const Handoff &h, int *keys, int ma
         __threadfence_system();
         flags[parity * max_ranks + h.rank] = (int) h.epoch;
     }
-    if (threadIdx.x == 0)
-        *h.ticket = 0;
 }
 
 // K2 prologue: the 12 merged keys into shared memory, from plain keys or from the local mailbox

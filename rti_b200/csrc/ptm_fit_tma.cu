@@ -49,6 +49,7 @@ struct TmaSmem {
 
 // One light's contribution to a lane's four pixels.
 //   word0 = Y0 Cb0 Cr0 Y1 | word1 = Cb1 Cr1 Y2 Cb2 | word2 = Cr2 Y3 Cb3 Cr3
+template <bool kSums = true>
 __device__ __forceinline__ void consume_light(const uint32_t *s32, const float4 *m, float (&acc)[4][PTM_NCOEF],
                                               unsigned (&ev)[3], unsigned (&od)[3]) {
     const unsigned w0 = s32[0], w1 = s32[1], w2 = s32[2];
@@ -76,12 +77,24 @@ __device__ __forceinline__ void consume_light(const uint32_t *s32, const float4 
         asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[p][2]), "=f"(acc[p][3]) : "l"(c23));
         asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[p][4]), "=f"(acc[p][5]) : "l"(c45));
     }
-    ev[0] += w0;
-    ev[1] += w1;
-    ev[2] += w2;
-    od[0] += __byte_perm(w0, 0, 0x4341);
-    od[1] += __byte_perm(w1, 0, 0x4341);
-    od[2] += __byte_perm(w2, 0, 0x4341);
+    if (kSums) {
+        ev[0] += w0;
+        ev[1] += w1;
+        ev[2] += w2;
+        od[0] += __byte_perm(w0, 0, 0x4341);
+        od[1] += __byte_perm(w1, 0, 0x4341);
+        od[2] += __byte_perm(w2, 0, 0x4341);
+    }
+}
+
+// Byte sums of TWO lights at once: three-operand adds (IADD3) halve the integer add count.
+__device__ __forceinline__ void sum_pair(const uint32_t *a, const uint32_t *b, unsigned (&ev)[3], unsigned (&od)[3]) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const unsigned wa = a[j], wb = b[j];
+        ev[j] = ev[j] + wa + wb;
+        od[j] = od[j] + __byte_perm(wa, 0, 0x4341) + __byte_perm(wb, 0, 0x4341);
+    }
 }
 
 // kDebug (tuning builds only, never selected by default): 1 = consumers skip the arithmetic
@@ -103,11 +116,8 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
     float4 *m_s = reinterpret_cast<float4 *>(smem + Smem::matrix);
 
     const unsigned n = a.n_lights;
-    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
-        const float *M = a.M;
-        m_s[2 * i] = make_float4(M[i], M[n + i], M[2 * n + i], M[3 * n + i]);
-        m_s[2 * i + 1] = make_float4(M[4 * n + i], M[5 * n + i], 0.f, 0.f);
-    }
+    // a programmatically dependent K2 (the fused encode) may be scheduled as soon as SM resources free up
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
@@ -121,6 +131,16 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
     const unsigned n_chunks = (n + L - 1) / L;
     Extrema ext;
     ext.init();
+
+    if (warp != kConsumerWarps) {
+        // consumers fetch the pinv table while the producer already streams the first stages
+        for (unsigned i = threadIdx.x; i < n; i += kConsumers) {
+            const float *M = a.M;
+            m_s[2 * i] = make_float4(M[i], M[n + i], M[2 * n + i], M[3 * n + i]);
+            m_s[2 * i + 1] = make_float4(M[4 * n + i], M[5 * n + i], 0.f, 0.f);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+    }
 
     if (warp == kConsumerWarps) {
         // ------------------------------------------------------------ producer
@@ -170,10 +190,15 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
                 if (kDebug == 1) {
                     ev[0] += buf[0];
                 } else if (cnt == L) {
-                    // straight-line body: all loads of the stage can be hoisted, adds pair into IADD3
+                    // straight-line body: all loads of the stage can be hoisted; byte sums go pairwise
 #pragma unroll
-                    for (unsigned l = 0; l < L; ++l)
-                        consume_light(buf + l * (kTileBytes / 4), m_s + 2 * (l0 + l), acc, ev, od);
+                    for (unsigned l = 0; l + 1 < L; l += 2) {
+                        consume_light<false>(buf + l * (kTileBytes / 4), m_s + 2 * (l0 + l), acc, ev, od);
+                        consume_light<false>(buf + (l + 1) * (kTileBytes / 4), m_s + 2 * (l0 + l + 1), acc, ev, od);
+                        sum_pair(buf + l * (kTileBytes / 4), buf + (l + 1) * (kTileBytes / 4), ev, od);
+                    }
+                    if (L & 1)
+                        consume_light(buf + (L - 1) * (kTileBytes / 4), m_s + 2 * (l0 + L - 1), acc, ev, od);
                 } else {
                     for (unsigned l = 0; l < cnt; ++l)
                         consume_light(buf + l * (kTileBytes / 4), m_s + 2 * (l0 + l), acc, ev, od);

@@ -60,7 +60,7 @@ quantise_kernel(const float *__restrict__ coeffs, size_t n_float4, size_t tail_f
 #pragma unroll
         for (int u = 0; u < kQuantUnroll; ++u) {
             const size_t i = kConsume ? n_float4 - 1 - (q + u * step) : q + u * step;
-            v[u] = kConsume ? __ldcg(src + i) : __ldcs(src + i);
+            v[u] = __ldcg(src + i);
         }
 #pragma unroll
         for (int u = 0; u < kQuantUnroll; ++u) {
@@ -76,7 +76,7 @@ quantise_kernel(const float *__restrict__ coeffs, size_t n_float4, size_t tail_f
     }
     for (; q < n_float4; q += step) {
         const size_t i = kConsume ? n_float4 - 1 - q : q;
-        const float4 v = __ldcs(src + i);
+        const float4 v = __ldcg(src + i);
         const unsigned b0 = clip_u8(__fadd_rn(__fmul_rn(v.x, inv[0]), bias[0]));
         const unsigned b1 = clip_u8(__fadd_rn(__fmul_rn(v.y, inv[1]), bias[1]));
         const unsigned b2 = clip_u8(__fadd_rn(__fmul_rn(v.z, inv[2]), bias[2]));
@@ -140,7 +140,24 @@ cudaError_t launch_quantise(const float *coeffs, size_t pixels, const KeySource 
     // pixels % 16 == 0.  Anything else takes the plain forward kernel.
     if (consume && n_float4 % 24 == 0 && n_float4 > 0 && (uintptr_t) coeffs % 128 == 0)
         quantise_kernel<true><<<grid, kQuantThreads, 0, st>>>(coeffs, n_float4, n_float4 * 4, n_floats, keys, bytes, sb);
-    else
+    else if (keys.mailbox != nullptr) {
+        // Fused hand-off: K2 waits for the keys in its prologue (mailbox flags), so it may be launched
+        // programmatically dependent on K1 -- its blocks become resident while K1 drains and the launch
+        // latency disappears from the critical path.  K1 issues griddepcontrol.launch_dependents at its
+        // start; K2 never reads K1's output before the flags are up (acquire loads + L1-bypassing reads).
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kQuantThreads);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const size_t tail_first = n_float4 * 4;
+        return cudaLaunchKernelEx(&cfg, quantise_kernel<false>, coeffs, n_float4, tail_first, n_floats, keys, bytes, sb);
+    } else
         quantise_kernel<false><<<grid, kQuantThreads, 0, st>>>(coeffs, n_float4, n_float4 * 4, n_floats, keys, bytes, sb);
     return cudaGetLastError();
 }
