@@ -77,6 +77,25 @@ int ptmb_host_unregister (const void *host);
  * major, HOST pointer.  Copied to the device; valid for all later fits. */
 int ptmb_set_matrix (ptmb_ctx_t *ctx, const float *M, unsigned n_lights);
 
+/* Which kernels serve the fits (both produce the reference's results within the same bars):
+ *   PTMB_ENGINE_FFMA    FP32 FMA streaming kernels (ptm_fit_tma*.cu)
+ *   PTMB_ENGINE_MMA     byte-wise integer GEMM on the tensor cores (ptm_fit_mma.cu): the
+ *                       pseudo-inverse as 32-bit fixed point, exact integer dot products, one rounding
+ *   PTMB_ENGINE_DEFAULT the library's choice per format (environment PTM_FIT_ENGINE=ffma|mma overrides)
+ * Layouts an engine cannot take (alignment, light count) fall through to the other GPU kernels. */
+#define PTMB_ENGINE_DEFAULT 0
+#define PTMB_ENGINE_FFMA    1
+#define PTMB_ENGINE_MMA     2
+int ptmb_set_fit_engine (ptmb_ctx_t *ctx, int engine);
+/* launches of the tensor-core kernel by this process so far (tests use it to prove which engine ran) */
+unsigned long long ptmb_mma_launches (void);
+/* Host only (no GPU needed): the B operand of the tensor-core engine for a 6 x n_lights matrix --
+ * balanced base-256 digits of round(M * 2^F_k), as the shared-memory image
+ * [n_lights/16 chunks][4 column groups][8 columns][16 lights]; column 4k+j = digit j of coefficient k,
+ * column 24 = ones.  scale[k] = 2^-F_k.  image_bytes >= 32 * kpad. */
+int ptmb_mma_pack_digits (const float *M, unsigned n_lights, int8_t *image, size_t image_bytes,
+                          float *scale, unsigned *kpad);
+
 /* Reset keys to the reference's initial extrema (min = FLT_MAX, max = -FLT_MAX,
  * rti-builder/ptmlib.c:826-827). */
 int ptmb_keys_init (ptmb_ctx_t *ctx, int32_t *keys_dev);

@@ -41,6 +41,9 @@ _SIGNATURES = {
     "ptmb_host_register": ([_vp, _sz], _int),
     "ptmb_host_unregister": ([_vp], _int),
     "ptmb_set_matrix": ([_vp, _vp, C.c_uint], _int),
+    "ptmb_set_fit_engine": ([_vp, _int], _int),
+    "ptmb_mma_launches": ([], C.c_ulonglong),
+    "ptmb_mma_pack_digits": ([_vp, C.c_uint, _vp, _sz, _vp, _vp], _int),
     "ptmb_keys_init": ([_vp, _vp], _int),
     "ptmb_fit_lrgb": ([_vp, _vp, _int, _sz, _sz, _vp, _vp, _vp], _int),
     "ptmb_fit_rgb": ([_vp, _vp, _int, _sz, _sz, _vp, _sz, _vp], _int),

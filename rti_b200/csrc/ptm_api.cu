@@ -103,6 +103,7 @@ void ptmb_destroy(ptmb_ctx_t *c) {
     cudaStreamSynchronize(c->stream);
     encode_scratch_release(c);
     cudaFree(c->M_dev);
+    cudaFree(c->digits_dev);
     cudaFree(c->keys_dev);
     cudaFree(c->sb_dev);
     cudaFree(c->ticket_dev);
@@ -186,6 +187,42 @@ int ptmb_set_matrix(ptmb_ctx_t *c, const float *M, unsigned n_lights) {
     c->magic = n_lights == 1 ? 0u : (unsigned) ((1ull << 32) / n_lights) + 1u;
     CK(cudaMemcpyAsync(c->M_dev, c->M_host.data(), c->M_host.size() * sizeof(float), cudaMemcpyHostToDevice,
                        c->stream));
+    // the same matrix as fixed-point digits for the tensor-core engine
+    std::vector<int8_t> image;
+    c->digits_ok = ptm::pack_mma_digits(c->M_host.data(), n_lights, image, c->digit_scale, &c->kpad);
+    if (c->digits_ok) {
+        if (image.size() > c->digits_cap) {
+            CK(cudaStreamSynchronize(c->stream));
+            CK(cudaFree(c->digits_dev));
+            c->digits_dev = nullptr;
+            c->digits_cap = 0;
+            CK(cudaMalloc(&c->digits_dev, image.size()));
+            c->digits_cap = image.size();
+        }
+        c->digits_host.swap(image);
+        CK(cudaMemcpyAsync(c->digits_dev, c->digits_host.data(), c->digits_host.size(), cudaMemcpyHostToDevice,
+                           c->stream));
+    }
+    return 0;
+}
+
+int ptmb_mma_pack_digits(const float *M, unsigned n_lights, int8_t *image, size_t image_bytes, float *scale,
+                         unsigned *kpad) {
+    REQUIRE(M && image && scale && kpad, "NULL argument");
+    std::vector<int8_t> img;
+    if (!ptm::pack_mma_digits(M, n_lights, img, scale, kpad))
+        return fail("ptmb_mma_pack_digits", "matrix not representable (non-finite entries or more than 224 lights)");
+    REQUIRE(image_bytes >= img.size(), "image buffer too small (needs 32 bytes per light rounded up to 32 lights)");
+    memcpy(image, img.data(), img.size());
+    return 0;
+}
+
+unsigned long long ptmb_mma_launches(void) { return ptm::mma_launch_count(); }
+
+int ptmb_set_fit_engine(ptmb_ctx_t *c, int engine) {
+    REQUIRE(c, "ctx is NULL");
+    REQUIRE(engine >= PTMB_ENGINE_DEFAULT && engine <= PTMB_ENGINE_MMA, "unknown engine");
+    c->engine = engine;
     return 0;
 }
 
@@ -212,6 +249,10 @@ static int make_fit_args(ptmb_ctx_t *c, const void *stack_dev, size_t image_stri
     a.rgb = nullptr;
     a.keys = nullptr;
     a.handoff = ptm::KeyHandoff{};
+    a.digits = c->digits_ok ? c->digits_dev : nullptr;
+    memcpy(a.digit_scale, c->digit_scale, sizeof(a.digit_scale));
+    a.kpad = c->kpad;
+    a.engine = c->engine;
     return 0;
 }
 
@@ -342,9 +383,10 @@ int ptmb_encode_lrgb_dev(ptmb_ctx_t *c, ptmb_xchg_t *x, const void *stack_dev, i
         for (int r = 0; r < a.handoff.world; ++r)
             a.handoff.mailbox[r] = x ? x->mailbox[r] : c->mailbox_dev;
         // the hand-off may only ride on a launch that covers every pixel of the slab
-        const size_t rem = pixels % 1024;
-        const bool whole = rem % 16 == 0;
-        if (whole)
+        const bool mma = ptm::resolve_engine(a.engine, ptm::kDefaultEngineLrgbU8) == 2;
+        if (mma && (pixels % 128) % 16 == 0)
+            CK(ptm::launch_fit_mma(a, 1, c->sm_count, c->stream, &done));
+        if (done == 0 && (pixels % 1024) % 16 == 0)
             CK(ptm::launch_fit_lrgb_tma(a, c->sm_count, c->stream, &done));
         if (done == pixels) {
             if (x)

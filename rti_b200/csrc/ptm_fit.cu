@@ -362,6 +362,19 @@ static inline unsigned grid_for(size_t items, unsigned threads, int sm_count, in
     return (unsigned) (want < cap ? want : cap);
 }
 
+// Which engine serves a fit: the caller's explicit choice, else PTM_FIT_ENGINE (ffma | mma),
+// else the per-format default.  1 = FFMA kernels, 2 = tensor-core kernel.
+int resolve_engine(int requested, int format_default) {
+    if (requested == 1 || requested == 2)
+        return requested;
+    static int env = -1;
+    if (env < 0) {
+        const char *v = getenv("PTM_FIT_ENGINE");
+        env = !v ? 0 : !strcmp(v, "mma") ? 2 : !strcmp(v, "ffma") ? 1 : 0;
+    }
+    return env ? env : format_default;
+}
+
 cudaError_t launch_keys_init(int *keys, cudaStream_t st) {
     keys_init_kernel<<<1, 32, 0, st>>>(keys);
     return cudaGetLastError();
@@ -384,9 +397,14 @@ cudaError_t launch_fit_lrgb(const FitArgs &a, int sample_type, int sm_count, cud
         }
         return cudaGetLastError();
     }
-    // 1) whole 1024-pixel tiles through the streaming (bulk copy) kernel when the layout allows it
+    // 1) whole 1024-pixel tiles through the streaming (bulk copy) kernel when the layout allows it,
+    //    or whole 128-pixel units through the tensor-core kernel
     size_t done = 0;
-    cudaError_t e = launch_fit_lrgb_tma(a, sm_count, st, &done);
+    cudaError_t e = cudaSuccess;
+    if (resolve_engine(a.engine, kDefaultEngineLrgbU8) == 2)
+        e = launch_fit_mma(a, 1, sm_count, st, &done);
+    if (e == cudaSuccess && done == 0)
+        e = launch_fit_lrgb_tma(a, sm_count, st, &done);
     if (e != cudaSuccess)
         return e;
     // 2) otherwise 4-pixel groups through the register kernel (word-aligned layouts)
@@ -429,7 +447,11 @@ cudaError_t launch_fit_rgb(const FitArgs &a, int sample_type, int sm_count, cuda
         return cudaErrorInvalidValue;
     // 1) streaming kernel over whole tiles (+ a 16-pixel-granular partial tile)
     size_t done = 0;
-    cudaError_t e = launch_fit_rgb_tma(a, sm_count, st, &done);
+    cudaError_t e = cudaSuccess;
+    if (resolve_engine(a.engine, kDefaultEngineRgbU8) == 2)
+        e = launch_fit_mma(a, 0, sm_count, st, &done);
+    if (e == cudaSuccess && done == 0)
+        e = launch_fit_rgb_tma(a, sm_count, st, &done);
     if (e != cudaSuccess)
         return e;
     // 2) 4-pixel groups through the register kernel for word-aligned layouts

@@ -36,6 +36,14 @@ struct ptmb_ctx {
     float *M_dev = nullptr;
     unsigned n_lights = 0;
     unsigned magic = 0;
+    // tensor-core engine: B operand image of the current matrix (nullptr when not representable)
+    std::vector<int8_t> digits_host;
+    int8_t *digits_dev = nullptr;
+    size_t digits_cap = 0;
+    bool digits_ok = false;
+    float digit_scale[6] = {0, 0, 0, 0, 0, 0};
+    unsigned kpad = 0;
+    int engine = 0;
     int *keys_dev = nullptr;                 // scratch for the host-buffer entry points
     ptmb_scale_bias_t *sb_dev = nullptr;
     std::vector<float> light_host;

@@ -4,6 +4,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <vector>
 
 namespace ptm {
 
@@ -49,6 +50,11 @@ struct FitArgs {
     uint8_t *rgb;           // [pixels][3] (LRGB only)
     int *keys;              // [12]
     KeyHandoff handoff;     // optional (ticket == nullptr: none)
+    // tensor-core engine (ptm_fit_mma.cu): fixed-point digits of M as the B operand image, device
+    const int8_t *digits;   // nullptr = not available for this matrix
+    float digit_scale[6];   // 2^-F_k
+    unsigned kpad;          // lights rounded up to 32
+    int engine;             // PTMB_ENGINE_*: 0 = default choice, 1 = FFMA kernels, 2 = tensor-core kernel
 };
 
 struct RelightArgs {
@@ -61,10 +67,17 @@ struct RelightArgs {
     uint8_t *out;             // [n_dirs][height][width][3]
 };
 
+bool pack_mma_digits(const float *M, unsigned n_lights, std::vector<int8_t> &image, float *scale, unsigned *kpad_out);
+// per-format default engines (1 = FFMA kernels, 2 = tensor-core kernel), see DESIGN.md
+constexpr int kDefaultEngineLrgbU8 = 1;
+constexpr int kDefaultEngineRgbU8 = 1;
+int resolve_engine(int requested, int format_default);
 cudaError_t launch_keys_init(int *keys, cudaStream_t st);
 cudaError_t launch_fit_lrgb(const FitArgs &a, int sample_type, int sm_count, cudaStream_t st);
 cudaError_t launch_fit_lrgb_tma(const FitArgs &a, int sm_count, cudaStream_t st, size_t *done);
 cudaError_t launch_fit_u16_tma(const FitArgs &a, bool rgb, int sm_count, cudaStream_t st, size_t *done);
+unsigned long long mma_launch_count();
+cudaError_t launch_fit_mma(const FitArgs &a, int mode, int sm_count, cudaStream_t st, size_t *done);
 cudaError_t launch_fit_rgb_tma(const FitArgs &a, int sm_count, cudaStream_t st, size_t *done);
 cudaError_t launch_fit_rgb(const FitArgs &a, int sample_type, int sm_count, cudaStream_t st);
 cudaError_t launch_fit_channel(const void *samples, int sample_type, size_t pixel_stride, size_t image_stride,

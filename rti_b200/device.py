@@ -86,6 +86,14 @@ class Context:
         _lib.check(self._lib.ptmb_set_matrix(self._h, M.ctypes.data, M.shape[1]))
         self.n_lights = M.shape[1]
 
+    def set_fit_engine(self, engine):
+        """"default" | "ffma" (FP32 FMA streaming kernels) | "mma" (integer GEMM on the tensor cores)."""
+        code = {"default": 0, "ffma": 1, "mma": 2}[engine] if isinstance(engine, str) else int(engine)
+        _lib.check(self._lib.ptmb_set_fit_engine(self._h, code))
+
+    def mma_launches(self):
+        return int(self._lib.ptmb_mma_launches())
+
     def keys_init(self, keys):
         _lib.check(self._lib.ptmb_keys_init(self._h, _ptr(keys)))
 

@@ -75,7 +75,8 @@ class PtmEncoder:
     exchange: "p2p" (NVLink peer-memory mailboxes, falling back to NCCL if peers cannot be
     mapped), or "nccl" (int32 MAX all-reduce through torch.distributed)."""
 
-    def __init__(self, width, rows, M, planes=1, device=None, group=None, keep_coeffs=True, exchange="p2p"):
+    def __init__(self, width, rows, M, planes=1, device=None, group=None, keep_coeffs=True, exchange="p2p",
+                 engine="default"):
         assert torch.cuda.is_available(), "rti_b200 needs a CUDA device (no CPU fallback)"
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.width, self.rows, self.planes = int(width), int(rows), int(planes)
@@ -83,6 +84,7 @@ class PtmEncoder:
         self.group = group
         self.ctx = Context(self.device.index, stream=torch.cuda.current_stream(self.device).cuda_stream)
         self.ctx.set_matrix(M)
+        self.ctx.set_fit_engine(engine)
         self.n_lights = self.ctx.n_lights
         P = self.pixels
         dev = self.device

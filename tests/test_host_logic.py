@@ -63,3 +63,37 @@ def test_light_q14_matches_oracle():
     from oracle import oracle as O
     d = lights.dome1_lights()
     np.testing.assert_array_equal(light_q14(d), O.light_q14(d))
+
+
+def test_mma_digit_packing_reproduces_the_dot_product_exactly(oracle, dome1, M60):
+    """Host half of the tensor-core engine (rti_b200/csrc/ptm_fit_mma.cu:pack_mma_digits): the int8 digit
+    image, pushed through an integer GEMM in numpy exactly as tcgen05.mma kind::i8 would, gives the
+    dot product with M to within 2^-31 of each row's largest entry."""
+    import ctypes as C
+    from rti_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    for M in (M60, oracle.pinv(np.asarray(dome1)[:13]), (rng.standard_normal((6, 100)) * 1e-3).astype(np.float32)):
+        M = np.ascontiguousarray(M, dtype=np.float32)
+        n = M.shape[1]
+        kpad = C.c_uint()
+        image = np.zeros(32 * ((n + 31) // 32 * 32), dtype=np.int8)
+        scale = np.zeros(6, dtype=np.float32)
+        _lib.check(lib.ptmb_mma_pack_digits(M.ctypes.data, n, image.ctypes.data, image.nbytes, scale.ctypes.data,
+                                            C.byref(kpad)))
+        assert kpad.value == (n + 31) // 32 * 32
+        B = image.reshape(kpad.value // 16, 4, 8, 16).transpose(0, 3, 1, 2).reshape(kpad.value, 32).astype(np.int64)
+        assert (B[n:] == 0).all() and (B[:n, 24] == 1).all() and (B[:, 25:] == 0).all()
+        y = rng.integers(0, 256, size=(50, kpad.value)).astype(np.int64)      # padding lights hold garbage
+        D = y @ B
+        np.testing.assert_array_equal(D[:, 24], y[:, :n].sum(1))
+        for k in range(6):
+            t = (D[:, 4 * k] << 24) + (D[:, 4 * k + 1] << 16) + (D[:, 4 * k + 2] << 8) + D[:, 4 * k + 3]
+            got = t.astype(np.float64) * float(scale[k])
+            want = y[:, :n].astype(np.float64) @ M[k].astype(np.float64)
+            tol = 2.0 ** -31 * np.abs(M[k]).max() * y[:, :n].sum(1)
+            assert (np.abs(got - want) <= tol).all()
+    bad = M60.copy()
+    bad[2, 5] = np.inf
+    assert lib.ptmb_mma_pack_digits(bad.ctypes.data, 60, image.ctypes.data, image.nbytes, scale.ctypes.data,
+                                    C.byref(kpad)) != 0
