@@ -76,6 +76,7 @@ struct MmaArgs {
     unsigned n_units;
     unsigned tail_px;         // pixels of the last unit when it is partial, else 0
     unsigned row_bytes;       // bytes of one image that the units cover
+    unsigned grouped;         // 1: whole units are loaded light-group-major (see the producer)
 };
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
@@ -92,6 +93,19 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t
         "}\n" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
         : "memory");
+}
+
+// one lane of a converged warp (the issue code stays warp-uniform, so descriptors live in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xFFFFFFFF;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
@@ -126,6 +140,24 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar,
+                                            uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_addr(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3,
+                                            uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_addr(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+        : "memory");
+}
+
 __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
                  "r"(smem_addr(src_smem)), "r"(bytes)
@@ -148,9 +180,12 @@ __device__ __forceinline__ long long digits_to_int(const int *d) {
 }  // namespace
 
 // kMode: 0 = RGB formats, uint8; 1 = LRGB, uint8; 2 = RGB formats, uint16; 3 = LRGB, uint16
-template <int kMode, int G>
+// kDebug (tuning builds, never the default): 1 = epilogue only drains TMEM (load + MMA ceiling),
+// 2 = additionally no MMAs are issued (TMA delivery ceiling), 3 = MMAs and drain but no loads (MMA ceiling)
+template <int kMode, int G, int kDebug = 0>
 __global__ void __launch_bounds__(64 + 128 * G, 1)
-fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, FitArgs a, MmaArgs m) {
+fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_grp,
+               const __grid_constant__ CUtensorMap tmap_rem, FitArgs a, MmaArgs m) {
     constexpr bool kLrgb = (kMode & 1) != 0;
     constexpr bool k16 = kMode >= 2;
     constexpr unsigned kUnitPx = k16 ? 64 : 128;
@@ -207,54 +242,94 @@ fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, FitArgs a, MmaArgs m) {
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            const uint64_t policy = l2_policy_evict_first();
-            unsigned s = 0, ph = 0;
-            for (unsigned u = blockIdx.x; u < m.n_units; u += gridDim.x) {
-                const unsigned byte0 = u * kUnitBytes;
-                const unsigned left = m.row_bytes - byte0;
-                const unsigned nblk = left >= (unsigned) kUnitBytes ? kUnitBlocks : (left + kBlk - 1) / kBlk;
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full[s], nblk * kBlk * a.n_lights);
-                for (unsigned c = 0; c < nblk; ++c)
-                    tma_load_2d(ring + (size_t) s * stage_bytes + (size_t) c * blk_bytes, &tmap,
-                                (int) (byte0 + c * kBlk), 0, &full[s], policy);
-                if (++s == m.stages) {
-                    s = 0;
-                    ph ^= 1;
+        // (the whole warp runs the loop converged; one elected lane issues)
+        const uint64_t policy = l2_policy_evict_first();
+        const unsigned groups = a.n_lights / 8, rem = a.n_lights % 8;
+        unsigned s = 0, ph = 0;
+        for (unsigned u = blockIdx.x; u < m.n_units; u += gridDim.x) {
+            const unsigned byte0 = u * kUnitBytes;
+            const unsigned left = m.row_bytes - byte0;
+            const unsigned nblk = left >= (unsigned) kUnitBytes ? kUnitBlocks : (left + kBlk - 1) / kBlk;
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t *dst = ring + (size_t) s * stage_bytes;
+            if (elect_one()) {
+                if (kDebug == 3) {
+                    mbar_arrive(&full[s]);
+                } else if (m.grouped && left >= (unsigned) kUnitBytes) {
+                    // Whole unit, light-group-major: one box = [8-light group][column block][8 lights][128 B],
+                    // so the three 128-byte pieces of a light are requested 8 pieces apart (DRAM row hits)
+                    // instead of a whole light set apart.  Stage layout [group][block][8 x 128 B swizzle atom].
+                    mbar_arrive_expect_tx(&full[s], (groups + (rem ? 1 : 0)) * (kUnitBytes * 8));
+                    if (groups)
+                        tma_load_4d(dst, &tmap_grp, 0, 0, (int) (u * kUnitBlocks), 0, &full[s], policy);
+                    if (rem)
+                        tma_load_3d(dst + (size_t) groups * (kUnitBytes * 8), &tmap_rem, 0, 0, (int) (u * kUnitBlocks),
+                                    &full[s], policy);
+                } else {
+                    mbar_arrive_expect_tx(&full[s], nblk * kBlk * a.n_lights);
+                    for (unsigned c = 0; c < nblk; ++c)
+                        tma_load_2d(dst + (size_t) c * blk_bytes, &tmap, (int) (byte0 + c * kBlk), 0, &full[s], policy);
                 }
+            }
+            __syncwarp();
+            if (++s == m.stages) {
+                s = 0;
+                ph ^= 1;
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t ring_a = smem_addr(ring), b_a = smem_addr(bdig);
-            const unsigned ksteps = m.kpad / 32;
-            unsigned s = 0, ph = 0, i = 0;
-            for (unsigned u = blockIdx.x; u < m.n_units; u += gridDim.x, ++i) {
-                const unsigned left = m.row_bytes - u * kUnitBytes;
-                const unsigned nblk = left >= (unsigned) kUnitBytes ? kUnitBlocks : (left + kBlk - 1) / kBlk;
-                const unsigned b = i % kAccBufs, use = i / kAccBufs;
-                mbar_wait(&tempty[b], (use & 1) ^ 1);
-                mbar_wait(&full[s], ph);
-                tc_fence_after();
-                for (unsigned c = 0; c < nblk; ++c) {
-                    const uint32_t d = tmem_base + b * kAccCols + c * kNB;
-                    const uint32_t a0 = ring_a + s * stage_bytes + c * blk_bytes;
-                    for (unsigned kk = 0; kk < ksteps; ++kk) {
-                        // A: 32 lights = 4 swizzle atoms of 8 rows x 128 B (SBO 1024); B: two 16-byte
-                        // K chunks 512 B apart (LBO), 8-column groups 128 B apart (SBO)
-                        const uint64_t ad = smem_desc(a0 + kk * 4096, 1024, 1024, 2);
-                        const uint64_t bd = smem_desc(b_a + kk * 1024, 512, 128, 0);
-                        mma_i8(d, ad, bd, kk != 0);
+        // (whole warp converged, one elected lane issues; descriptors advance by adding to their low word)
+        const uint32_t ring_a = smem_addr(ring);
+        const unsigned ksteps = m.kpad / 32;
+        const uint64_t bdesc0 = smem_desc(smem_addr(bdig), 512, 128, 0);
+        unsigned s = 0, ph = 0, i = 0;
+        for (unsigned u = blockIdx.x; u < m.n_units; u += gridDim.x, ++i) {
+            const unsigned left = m.row_bytes - u * kUnitBytes;
+            const unsigned nblk = left >= (unsigned) kUnitBytes ? kUnitBlocks : (left + kBlk - 1) / kBlk;
+            const unsigned b = i % kAccBufs, use = i / kAccBufs;
+            mbar_wait(&tempty[b], (use & 1) ^ 1);
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                // A: 32 lights = 4 swizzle atoms of 8 rows x 128 B (SBO = atom stride); B: two 16-byte K chunks
+                // 512 B apart (LBO), 8-column groups 128 B apart (SBO), 1024 B per 32 lights
+                const bool grp = m.grouped && left >= (unsigned) kUnitBytes;   // whole unit
+                const uint32_t atom_stride = grp ? kUnitBytes * 8 : 1024;   // between 8-light swizzle atoms
+                const uint32_t blk_stride = grp ? 1024u : blk_bytes;        // between column blocks of a stage
+                const uint64_t adesc0 = smem_desc(ring_a + s * stage_bytes, atom_stride, atom_stride, 2);
+                const uint32_t a_step = (4 * atom_stride) >> 4;
+                const uint32_t d0 = tmem_base + b * kAccCols;
+                if (kDebug != 2) {
+                    if (nblk == kUnitBlocks) {
+#pragma unroll
+                        for (int c = 0; c < kUnitBlocks; ++c) {
+                            uint64_t ad = adesc0 + ((c * blk_stride) >> 4), bd = bdesc0;
+                            mma_i8(d0 + c * kNB, ad, bd, 0);
+                            for (unsigned kk = 1; kk < ksteps; ++kk) {
+                                ad += a_step;
+                                bd += 1024 >> 4;
+                                mma_i8(d0 + c * kNB, ad, bd, 1);
+                            }
+                        }
+                    } else {
+                        for (unsigned c = 0; c < nblk; ++c) {
+                            uint64_t ad = adesc0 + ((c * blk_stride) >> 4), bd = bdesc0;
+                            for (unsigned kk = 0; kk < ksteps; ++kk) {
+                                mma_i8(d0 + c * kNB, ad, bd, kk != 0);
+                                ad += a_step;
+                                bd += 1024 >> 4;
+                            }
+                        }
                     }
                 }
                 mma_commit(&empty[s]);   // the stage may be refilled once these MMAs have read it
                 mma_commit(&tfull[b]);   // ... and the accumulators are complete
-                if (++s == m.stages) {
-                    s = 0;
-                    ph ^= 1;
-                }
+            }
+            __syncwarp();
+            if (++s == m.stages) {
+                s = 0;
+                ph ^= 1;
             }
         }
     } else {
@@ -280,7 +355,16 @@ fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, FitArgs a, MmaArgs m) {
             mbar_wait(&tfull[b], use & 1);
             tc_fence_after();
 
-            if (kMode == 0) {
+            if (kDebug != 0) {
+                int v[32];
+                tmem_ld32(lane_base + b * kAccCols, v);
+                if (v[0] == 0x7FFFFFFF)
+                    ext.mn[0] = 0.f;
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(&tempty[b]);
+            } else if (kMode == 0) {
                 // every byte row is a sample row of its own fit
                 float f[kUnitBlocks][PTM_NCOEF];
 #pragma unroll
@@ -373,6 +457,62 @@ fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, FitArgs a, MmaArgs m) {
                     bulk_s2g(a.rgb + px0 * 3, stg + kStagePlane, valid * 3);
                     bulk_commit();
                 }
+            } else if (kMode == 2) {
+                // 16-bit samples (ptm_fit_poly_uint semantics, rti-builder/ptmlib.c:727-760): byte rows come
+                // in (low, high) pairs on neighbouring lanes, sample = lo + 256 * hi, so the exact integer
+                // dot products combine the same way.  The even lane finishes coefficients 0..2 of the
+                // pair's sample, the odd lane 3..5.
+                const bool odd = (r & 1) != 0;
+                float f[kUnitBlocks][3];
+#pragma unroll
+                for (int c = 0; c < kUnitBlocks; ++c) {
+                    int v[32];
+                    tmem_ld32(lane_base + b * kAccCols + c * kNB, v);
+                    long long t[PTM_NCOEF];
+#pragma unroll
+                    for (int k = 0; k < PTM_NCOEF; ++k)
+                        t[k] = digits_to_int(&v[4 * k]);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const long long send = odd ? t[j] : t[3 + j];
+                        const long long recv = __shfl_xor_sync(0xFFFFFFFFu, send, 1);
+                        const long long whole = odd ? recv + 256 * t[3 + j] : t[j] + 256 * recv;
+                        f[c][j] = __fmul_rn(__ll2float_rn(whole), odd ? sc[3 + j] : sc[j]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(&tempty[b]);
+                if (issuer)
+                    bulk_wait_read();
+                group_sync(1 + g);
+#pragma unroll
+                for (int c = 0; c < kUnitBlocks; ++c) {
+                    const unsigned sg = (c * kBlk + r) >> 1, px = sg / 3, ch = sg - 3 * px;
+                    if (ch == 0 && px < valid) {
+#pragma unroll
+                        for (int k = 0; k < PTM_NCOEF; ++k) {
+                            if ((k >= 3) == odd) {
+                                ext.mn[k] = fminf(ext.mn[k], f[c][k % 3]);
+                                ext.mx[k] = fmaxf(ext.mx[k], f[c][k % 3]);
+                            }
+                        }
+                    }
+                    float *row = reinterpret_cast<float *>(stg + ch * kStagePlane + px * 24 + (odd ? 12 : 0));
+                    row[0] = f[c][0];
+                    row[1] = f[c][1];
+                    row[2] = f[c][2];
+                }
+                fence_async_smem();
+                group_sync(1 + g);
+                if (issuer) {
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch)
+                        bulk_s2g(a.coeffs + (size_t) ch * a.plane_stride + px0 * PTM_NCOEF, stg + ch * kStagePlane,
+                                 valid * 24);
+                    bulk_commit();
+                }
             }
         }
         if (issuer) {
@@ -459,8 +599,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
     return fn;
 }
 
-template <int kMode, int G>
-static cudaError_t launch_mode(const CUtensorMap &map, const FitArgs &a, const MmaArgs &m, size_t smem, unsigned grid,
+template <int kMode, int G, int kDebug = 0>
+static cudaError_t launch_mode(const CUtensorMap *maps, const FitArgs &a, const MmaArgs &m, size_t smem, unsigned grid,
                                cudaStream_t st) {
     static bool configured[64];
     int dev = 0;
@@ -469,30 +609,30 @@ static cudaError_t launch_mode(const CUtensorMap &map, const FitArgs &a, const M
         return e;
     if (dev < 0 || dev >= 64)
         return cudaErrorInvalidDevice;
-    auto kern = fit_mma_kernel<kMode, G>;
+    auto kern = fit_mma_kernel<kMode, G, kDebug>;
     if (!configured[dev]) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
         if (e != cudaSuccess)
             return e;
         configured[dev] = true;
     }
-    kern<<<grid, 64 + 128 * G, smem, st>>>(map, a, m);
+    kern<<<grid, 64 + 128 * G, smem, st>>>(maps[0], maps[1], maps[2], a, m);
     return cudaGetLastError();
 }
 
-// mode: 0 = RGB u8, 1 = LRGB u8.  Covers whole 384-byte units (+ a 16-pixel-granular partial
+// mode: 0 = RGB u8, 1 = LRGB u8, 2 = RGB u16.  Covers whole 384-byte units (+ a 16-pixel-granular partial
 // last unit) and reports the pixels it covered through *done; 0 = layout not eligible.
 cudaError_t launch_fit_mma(const FitArgs &a, int mode, int sm_count, cudaStream_t st, size_t *done) {
     *done = 0;
-    if (mode != 0 && mode != 1)
+    if (mode < 0 || mode > 2)
         return cudaSuccess;
     if (!a.digits || a.kpad == 0 || a.kpad > 224 || a.n_lights > a.kpad)
         return cudaSuccess;
-    const unsigned unit_px = 128, px_bytes = 3;
+    const unsigned unit_px = mode == 2 ? 64 : 128, px_bytes = mode == 2 ? 6 : 3;
     const size_t row_bytes_all = a.pixels * px_bytes;
     bool ok = ((uintptr_t) a.stack % 16 == 0) && (a.image_stride % 16 == 0) && row_bytes_all < 0x7FFFFFFFull &&
               a.image_stride >= row_bytes_all;
-    if (mode == 0)
+    if (mode == 0 || mode == 2)
         ok = ok && a.coeffs && ((uintptr_t) a.coeffs % 16 == 0) && (a.plane_stride % 4 == 0);
     else
         ok = ok && ((uintptr_t) a.rgb % 16 == 0) && (a.coeffs == nullptr || (uintptr_t) a.coeffs % 16 == 0);
@@ -506,7 +646,12 @@ cudaError_t launch_fit_mma(const FitArgs &a, int mode, int sm_count, cudaStream_
     if (!encode)
         return cudaSuccess;
 
-    constexpr int G = 2;
+    static int variant = -1;
+    if (variant < 0) {
+        const char *v = getenv("PTM_MMA_VARIANT");   // tuning aid; the default is what ships
+        variant = v ? atoi(v) : 0;
+    }
+    const int G = variant == 1 ? 4 : 2;
     MmaArgs m;
     m.digits = a.digits;
     memcpy(m.scale, a.digit_scale, sizeof(m.scale));
@@ -524,7 +669,9 @@ cudaError_t launch_fit_mma(const FitArgs &a, int mode, int sm_count, cudaStream_
     m.stages = (unsigned) stages;
     const size_t smem = fixed - (2 * kMaxStages) * 8 + 2 * stages * 8 + stages * stage_bytes;
 
-    CUtensorMap map;
+    CUtensorMap maps[3];
+    CUtensorMap &map = maps[0];
+    memset(maps, 0, sizeof(maps));
     const cuuint64_t gdim[2] = {(cuuint64_t) m.row_bytes, (cuuint64_t) a.n_lights};
     const cuuint64_t gstride[1] = {(cuuint64_t) a.image_stride};
     const cuuint32_t box[2] = {(cuuint32_t) kBlk, (cuuint32_t) a.n_lights};
@@ -535,10 +682,68 @@ cudaError_t launch_fit_mma(const FitArgs &a, int mode, int sm_count, cudaStream_
     if (r != CUDA_SUCCESS)
         return cudaSuccess;   // not representable: the FFMA kernels take the slab
 
+    // light-group-major maps for whole units (see the producer): the 128-byte window and the column block
+    // index are separate dimensions over the same bytes; only whole column blocks are addressable, the
+    // partial last unit goes through the plain 2-D map above
+    static int load_mode = -1, l2_promo = -1;
+    if (load_mode < 0) {
+        const char *v = getenv("PTM_MMA_LOAD");
+        load_mode = v ? atoi(v) : 1;
+        const char *w = getenv("PTM_MMA_L2");
+        l2_promo = w ? atoi(w) : 128;
+    }
+    const CUtensorMapL2promotion promo = l2_promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                         : l2_promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                                         : l2_promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                                                          : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    m.grouped = 0;
+    const unsigned groups = a.n_lights / 8, rem_l = a.n_lights % 8;
+    const cuuint64_t whole_blocks = m.row_bytes / kBlk;
+    if (load_mode == 1 && whole_blocks >= (cuuint64_t) kUnitBlocks) {
+        bool ok2 = true;
+        if (groups) {
+            const cuuint64_t d4[4] = {(cuuint64_t) kBlk, 8, whole_blocks, groups};
+            const cuuint64_t s4[3] = {(cuuint64_t) a.image_stride, (cuuint64_t) kBlk, (cuuint64_t) a.image_stride * 8};
+            const cuuint32_t b4[4] = {(cuuint32_t) kBlk, 8, (cuuint32_t) kUnitBlocks, groups};
+            const cuuint32_t e4[4] = {1, 1, 1, 1};
+            ok2 = encode(&maps[1], CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t *>(a.stack), d4, s4, b4, e4,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+        if (ok2 && rem_l) {
+            const cuuint64_t d3[3] = {(cuuint64_t) kBlk, rem_l, whole_blocks};
+            const cuuint64_t s3[2] = {(cuuint64_t) a.image_stride, (cuuint64_t) kBlk};
+            const cuuint32_t b3[3] = {(cuuint32_t) kBlk, 8, (cuuint32_t) kUnitBlocks};
+            const cuuint32_t e3[3] = {1, 1, 1};
+            ok2 = encode(&maps[2], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
+                         const_cast<uint8_t *>(a.stack) + (size_t) groups * 8 * a.image_stride, d3, s3, b3, e3,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+        m.grouped = ok2 ? 1 : 0;
+    }
+    if (!m.grouped) {
+        maps[1] = maps[0];
+        maps[2] = maps[0];
+    }
+
     unsigned grid = (unsigned) sm_count;
     if ((size_t) grid > n_units)
         grid = (unsigned) n_units;
-    cudaError_t e = mode == 0 ? launch_mode<0, G>(map, a, m, smem, grid, st) : launch_mode<1, G>(map, a, m, smem, grid, st);
+    cudaError_t e;
+    switch (variant) {
+    case 1:
+        e = mode == 0 ? launch_mode<0, 4>(maps, a, m, smem, grid, st)
+            : mode == 1 ? launch_mode<1, 4>(maps, a, m, smem, grid, st) : launch_mode<2, 4>(maps, a, m, smem, grid, st);
+        break;
+    case 2: e = mode == 2 ? launch_mode<2, 2, 1>(maps, a, m, smem, grid, st) : launch_mode<1, 2, 1>(maps, a, m, smem, grid, st); break;
+    case 3: e = mode == 2 ? launch_mode<2, 2, 2>(maps, a, m, smem, grid, st) : launch_mode<1, 2, 2>(maps, a, m, smem, grid, st); break;
+    case 4: e = mode == 2 ? launch_mode<2, 2, 3>(maps, a, m, smem, grid, st) : launch_mode<1, 2, 3>(maps, a, m, smem, grid, st); break;
+    default:
+        e = mode == 0 ? launch_mode<0, 2>(maps, a, m, smem, grid, st)
+            : mode == 1 ? launch_mode<1, 2>(maps, a, m, smem, grid, st) : launch_mode<2, 2>(maps, a, m, smem, grid, st);
+        break;
+    }
     if (e == cudaSuccess) {
         *done = full_units * unit_px + tail_px;
         ++g_mma_launches;

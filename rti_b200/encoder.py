@@ -99,7 +99,7 @@ class PtmEncoder:
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.exchange_kind = "none" if not multi else ("p2p" if self.xchg is not None else "nccl")
         # fused LRGB encode: K1 + K2; otherwise keys-init, K1, K2 per plane
-        self.launches_per_encode = 2 if (self.planes == 1 and self.exchange_kind in ("none", "p2p")) else 2 + self.planes
+        self.launches_per_encode = 2 if (self.planes == 1 and self.exchange_kind in ("none", "p2p")) else 3
 
     def _use_current_stream(self):
         self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
@@ -126,10 +126,11 @@ class PtmEncoder:
             allreduce_keys(self.keys, self.group)
 
     def quantise(self):
-        """K2: scale/bias from the (global) keys, then bytes for every plane."""
-        for b in reversed(range(self.planes)):   # the plane written last is the one still in L2
-            self.ctx.quantise(self.coeffs[b], self.pixels, self.keys, self.coef_bytes[b],
-                              self.sb if b == 0 else None, consume=not self.keep_coeffs)
+        """K2: scale/bias from the (global) keys, then bytes for every plane.  The planes are contiguous
+        and share one scale/bias (rti-builder/ptmlib.c:867-880), so the RGB formats are one launch over
+        planes * pixels coefficient vectors."""
+        self.ctx.quantise(self.coeffs, self.pixels * self.planes, self.keys, self.coef_bytes, self.sb,
+                          consume=not self.keep_coeffs)
 
     def encode(self, stack):
         """fit -> exchange -> quantise.  LRGB with the peer (or no) exchange goes through the fused

@@ -42,8 +42,9 @@ def _ring_lights(n):
 
 
 # 128-pixel units: exactly one, one + tail of 16, many + tail, tail only, a width that leaves a
-# remainder for the generic kernel (pixels % 16 != 0), and enough units for several ring wraps
-SHAPES = [(128, 1), (48, 3), (16, 1), (64, 48), (72, 33), (37, 29), (80, 33), (512, 300)]
+# remainder for the generic kernel (pixels % 16 != 0), a tail whose third column block is partial
+# (112 x 2), and enough units for several ring wraps
+SHAPES = [(128, 1), (48, 3), (16, 1), (64, 48), (72, 33), (37, 29), (80, 33), (112, 2), (512, 300)]
 
 
 def eligible(W, H):
@@ -89,20 +90,25 @@ def test_lrgb_mma_vs_oracle(ctx, oracle, dome1, M60, W, H):
         assert_bytes_close(got["coef"], want["coef"], "LRGB coefficient bytes (mma) %dx%d" % (W, H), 0.02)
 
 
-@pytest.mark.parametrize("n", [12, 32, 33, 100, 224])
+@pytest.mark.parametrize("n", [12, 32, 33, 100, 128, 160, 192, 224])
 def test_mma_light_counts(ctx, oracle, n):
-    """K padding (lights rounded up to 32), one to seven MMA steps per column block."""
+    """K padding (lights rounded up to 32), one to seven MMA steps per column block; light groups
+    of 8 with and without a remainder group."""
     L = _ring_lights(n)
     M = oracle.pinv(L)
-    W, H = 72, 33
+    W, H = 80, 33                                     # 2640 px: 16-byte image pitch, 20 units + a tail
+    assert eligible(W, H)
     stack = oracle.synth_stack(0x4000 + n, 0, W, H, L)
     want = oracle.encode_lrgb(stack, M)
+    before = ctx.mma_launches()
     got = gpu_encode_lrgb(ctx, stack, M)
+    assert ctx.mma_launches() == before + 1
     np.testing.assert_array_equal(got["rgb"], want["rgb"])
     assert coeff_error(got["coeffs"], want["coeffs"], M, stack[..., 0], lrgb=True) <= 1e-5
     st3 = oracle.synth_stack(0x5000 + n, 1, W, H, L)
     w3 = oracle.encode_rgb(st3, M)
     g3 = gpu_encode_rgb(ctx, st3, M)
+    assert ctx.mma_launches() == before + 2
     for ch in range(3):
         assert coeff_error(g3["coeffs"][ch], w3["coeffs"][ch], M, st3[..., ch]) <= 1e-5
 
@@ -151,3 +157,32 @@ def test_mma_matches_ffma_engine_at_scale(ctx, ctx_ffma, oracle, dome1, M60):
         assert int(diff.max()) <= 1
         print("bytes differing between engines: %d of %d" % (int((diff != 0).sum()), diff.numel()))
         assert int((diff != 0).sum()) <= 0.01 * diff.numel()
+
+
+@pytest.mark.parametrize("W,H,n", [(64, 1, 60), (80, 33, 60), (72, 33, 100), (512, 150, 100), (48, 5, 224)])
+def test_rgb_u16_mma_vs_oracle(ctx, oracle, W, H, n):
+    """16-bit stacks (ptm_fit_poly_uint semantics): low and high byte rows combined in integers."""
+    from rti_b200.device import U16
+    L = _ring_lights(n)
+    M = oracle.pinv(L)
+    P = W * H
+    s16 = oracle.synth_stack(0x6000 + n + W, 1, W, H, L, dtype=np.uint16)
+    want = oracle.encode_rgb_u16(s16, M)
+    ctx.set_matrix(M)
+    coeffs = torch.empty((3, P, 6), dtype=torch.float32, device="cuda")
+    keys = torch.empty(12, dtype=torch.int32, device="cuda")
+    ctx.keys_init(keys)
+    before = ctx.mma_launches()
+    ctx.fit_rgb(dev(s16.view(np.int16)).view(torch.uint16), P * 6, P, coeffs, P * 6, keys, U16)
+    torch.cuda.synchronize()
+    assert ctx.mma_launches() == before + (1 if (P * 6) % 16 == 0 and P >= 16 else 0)
+    got = coeffs.cpu().numpy().reshape(3, H, W, 6)
+    for ch in range(3):
+        err = coeff_error(got[ch], want["coeffs"][ch], M, s16[..., ch])
+        print("plane %d normalised coefficient error %.3g" % (ch, err))
+        assert err <= 1e-5
+    from rti_b200.device import key_to_float
+    f = key_to_float(keys.cpu().numpy())
+    mm = np.concatenate([-f[:6], f[6:]])
+    p0 = want["coeffs"][0].reshape(-1, 6)
+    np.testing.assert_allclose(mm, np.concatenate([p0.min(0), p0.max(0)]), rtol=3e-5, atol=1e-2)

@@ -38,7 +38,7 @@ def main():
     M = ptm_svd(L)
     stack = torch.empty((n, H, W, 3), dtype=torch.uint8, device="cuda")
     for planes, mode, name in ((1, 0, "LRGB"), (3, 1, "RGB")):
-        for engine in ("ffma", "mma"):
+        for engine in os.environ.get("ENGINES", "ffma,mma").split(","):
             enc = PtmEncoder(W, H, M, planes=planes, engine=engine)
             enc.ctx.synth(0x5EED0001, mode, U8, 0, P, light_q14(L), stack, P * 3)
             before = enc.ctx.mma_launches()
