@@ -77,6 +77,7 @@ struct MmaArgs {
     unsigned tail_px;         // pixels of the last unit when it is partial, else 0
     unsigned row_bytes;       // bytes of one image that the units cover
     unsigned grouped;         // 1: whole units are loaded light-group-major (see the producer)
+    unsigned chunk;           // units per CTA when CTAs own consecutive units, 0 = units strided by the grid
 };
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
@@ -240,13 +241,19 @@ fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     Extrema ext;
     ext.init();
 
+    // which units this CTA owns: strided by the grid, or one run of consecutive units (the ring then holds
+    // several adjacent 384-byte pieces of every light: more DRAM row hits)
+    const unsigned u_first = m.chunk ? blockIdx.x * m.chunk : blockIdx.x;
+    const unsigned u_last = m.chunk ? min(m.n_units, u_first + m.chunk) : m.n_units;
+    const unsigned u_step = m.chunk ? 1u : gridDim.x;
+
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         // (the whole warp runs the loop converged; one elected lane issues)
         const uint64_t policy = l2_policy_evict_first();
         const unsigned groups = a.n_lights / 8, rem = a.n_lights % 8;
         unsigned s = 0, ph = 0;
-        for (unsigned u = blockIdx.x; u < m.n_units; u += gridDim.x) {
+        for (unsigned u = u_first; u < u_last; u += u_step) {
             const unsigned byte0 = u * kUnitBytes;
             const unsigned left = m.row_bytes - byte0;
             const unsigned nblk = left >= (unsigned) kUnitBytes ? kUnitBlocks : (left + kBlk - 1) / kBlk;
@@ -284,7 +291,7 @@ fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         const unsigned ksteps = m.kpad / 32;
         const uint64_t bdesc0 = smem_desc(smem_addr(bdig), 512, 128, 0);
         unsigned s = 0, ph = 0, i = 0;
-        for (unsigned u = blockIdx.x; u < m.n_units; u += gridDim.x, ++i) {
+        for (unsigned u = u_first; u < u_last; u += u_step, ++i) {
             const unsigned left = m.row_bytes - u * kUnitBytes;
             const unsigned nblk = left >= (unsigned) kUnitBytes ? kUnitBlocks : (left + kBlk - 1) / kBlk;
             const unsigned b = i % kAccBufs, use = i / kAccBufs;
@@ -346,7 +353,7 @@ fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             sc[k] = m.scale[k];
 
         unsigned i = 0;
-        for (unsigned u = blockIdx.x; u < m.n_units; u += gridDim.x, ++i) {
+        for (unsigned u = u_first; u < u_last; u += u_step, ++i) {
             if (i % G != g)
                 continue;
             const unsigned b = i % kAccBufs, use = i / kAccBufs;
@@ -730,6 +737,16 @@ cudaError_t launch_fit_mma(const FitArgs &a, int mode, int sm_count, cudaStream_
     unsigned grid = (unsigned) sm_count;
     if ((size_t) grid > n_units)
         grid = (unsigned) n_units;
+    static int sched = -1;
+    if (sched < 0) {
+        const char *v = getenv("PTM_MMA_SCHED");
+        sched = v ? atoi(v) : 1;
+    }
+    m.chunk = 0;
+    if (sched == 1) {
+        m.chunk = (unsigned) ((n_units + grid - 1) / grid);
+        grid = (unsigned) ((n_units + m.chunk - 1) / m.chunk);
+    }
     cudaError_t e;
     switch (variant) {
     case 1:
