@@ -16,6 +16,8 @@
 //                __fadd_rz(., 2^23), whose low mantissa byte is the truncated value -- no trip
 //                through the (quarter-rate) conversion unit.  For LRGB the lower clamp is applied
 //                once to L (the colour bytes are non-negative).
+#include <cstdlib>
+
 #include "ptm_device.cuh"
 #include "ptm_kernels.h"
 
@@ -120,6 +122,61 @@ relight_lrgb_x4_kernel(RelightArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// RGB formats, 4 consecutive pixels of an output row per thread (width % 4 == 0): three planes of
+// 24 B each, 72 unscaled coefficients in registers, 12 bytes = 3 words out per direction
+// (rti-builder/ptmlib.c:610-619: CLIP(POLY) per channel, both clamps needed).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRelightThreads, 2)
+relight_rgb_x4_kernel(RelightArgs a) {
+    extern __shared__ float light_s[];  // [n_dirs][8]: u^2 v^2 uv u v (1) pad pad
+    for (unsigned i = threadIdx.x; i < a.n_dirs * 8; i += blockDim.x)
+        light_s[i] = (i & 7) < PTM_NCOEF ? a.light[(i >> 3) * PTM_NCOEF + (i & 7)] : 0.f;
+    __syncthreads();
+
+    const size_t pixels = a.width * a.height;
+    const size_t groups = pixels / 4;
+    const size_t gw = a.width / 4;
+    float kb[PTM_NCOEF];
+#pragma unroll
+    for (int k = 0; k < PTM_NCOEF; ++k)
+        kb[k] = 8388608.0f + (float) a.bias[k];
+    for (size_t g = (size_t) blockIdx.x * blockDim.x + threadIdx.x; g < groups;
+         g += (size_t) gridDim.x * blockDim.x) {
+        const size_t y = g / gw, xg = g - y * gw;
+        const size_t p = (a.height - 1 - y) * a.width + xg * 4;
+        float u[3][4][PTM_NCOEF];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const uint2 *c2 = reinterpret_cast<const uint2 *>(a.plane[ch] + p * PTM_NCOEF);
+            const uint2 cw[3] = {__ldg(c2), __ldg(c2 + 1), __ldg(c2 + 2)};
+            const uint32_t cb[6] = {cw[0].x, cw[0].y, cw[1].x, cw[1].y, cw[2].x, cw[2].y};
+#pragma unroll
+            for (int j = 0; j < 24; ++j) {
+                const float m = __uint_as_float(__byte_perm(cb[j >> 2], 0x4B000000u, 0x7650u + (j & 3)));
+                u[ch][j / 6][j % 6] = __fmul_rn(a.scale[j % 6], __fsub_rn(m, kb[j % 6]));
+            }
+        }
+        uint32_t *dst = reinterpret_cast<uint32_t *>(a.out + g * 12);
+        const size_t dir_words = pixels * 3 / 4;
+        for (unsigned d = 0; d < a.n_dirs; ++d) {
+            const float4 la = *reinterpret_cast<const float4 *>(light_s + d * 8);
+            const float l4 = light_s[d * 8 + 4];
+            const float l[5] = {la.x, la.y, la.z, la.w, l4};
+            unsigned b[12];
+#pragma unroll
+            for (int px = 0; px < 4; ++px)
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+                    b[px * 3 + ch] = clip_bits(poly_eval(u[ch][px], l));
+            __stcs(dst + 0, pack4(b[0], b[1], b[2], b[3]));
+            __stcs(dst + 1, pack4(b[4], b[5], b[6], b[7]));
+            __stcs(dst + 2, pack4(b[8], b[9], b[10], b[11]));
+            dst += dir_words;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Generic path: one pixel per thread, any width; LRGB or RGB planes.
 // ---------------------------------------------------------------------------
 template <bool kLrgb>
@@ -205,6 +262,21 @@ cudaError_t launch_relight(const RelightArgs &a, bool lrgb, int sm_count, cudaSt
         size_t cap = (size_t) sm_count * 8;
         unsigned grid = (unsigned) (want < cap ? want : cap);
         relight_lrgb_x4_kernel<<<grid, kRelightThreads, (size_t) a.n_dirs * 8 * sizeof(float), st>>>(a);
+        return cudaGetLastError();
+    }
+    static int x4_rgb = -1;
+    if (x4_rgb < 0) {
+        const char *v = getenv("PTM_RELIGHT_RGB_X4");   // tuning aid: 0 = one pixel per thread
+        x4_rgb = v ? atoi(v) : 1;
+    }
+    const bool rgb4 = x4_rgb && !lrgb && small_bias && a.width % 4 == 0 && ((uintptr_t) a.plane[0] % 8 == 0) &&
+                      ((uintptr_t) a.plane[1] % 8 == 0) && ((uintptr_t) a.plane[2] % 8 == 0) &&
+                      ((uintptr_t) a.out % 4 == 0);
+    if (rgb4) {
+        size_t want4 = (pixels / 4 + kRelightThreads - 1) / kRelightThreads;
+        size_t cap4 = (size_t) sm_count * 2;
+        unsigned grid4 = (unsigned) (want4 < cap4 ? want4 : cap4);
+        relight_rgb_x4_kernel<<<grid4, kRelightThreads, (size_t) a.n_dirs * 8 * sizeof(float), st>>>(a);
         return cudaGetLastError();
     }
     size_t want = (pixels + kRelightThreads - 1) / kRelightThreads;

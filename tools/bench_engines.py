@@ -34,6 +34,12 @@ def main():
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = json.load(open(pk))["hbm_gbs"] if os.path.exists(pk) else 6650.0
     L = lights.dome1_lights()
+    if os.environ.get("N_LIGHTS"):          # any other light count: a spiral of that many directions
+        import numpy as np
+        nl = int(os.environ["N_LIGHTS"])
+        th = np.arange(nl) * 2.399963
+        r = 0.15 + 0.8 * (np.arange(nl) + 0.5) / nl
+        L = np.stack([r * np.cos(th), r * np.sin(th), np.sqrt(1 - r * r)], 1).astype(np.float32)
     n, P = len(L), W * H
     M = ptm_svd(L)
     stack = torch.empty((n, H, W, 3), dtype=torch.uint8, device="cuda")

@@ -52,6 +52,37 @@ def main():
         print(json.dumps({"directions": D, "ms": ms, "pixel_directions_per_s": pd,
                           "achieved_GBs": pd * bytes_pd / 1e9, "frac_of_hbm_peak": pd * bytes_pd / 1e9 / peak}))
         del out
+    # RGB-format PTM (three coefficient planes, CLIP(POLY) per channel): (18 + 3 D) / D bytes per pixel-direction
+    del enc
+    torch.cuda.empty_cache()
+    stack = torch.empty((60, H, W, 3), dtype=torch.uint8, device="cuda")
+    enc = PtmEncoder(W, H, M, planes=3)
+    enc.ctx.synth(0x5EED0001, 1, U8, 0, P, light_q14(L), stack, P * 3)
+    enc.encode(stack)
+    torch.cuda.synchronize()
+    scale, bias = enc.scale_bias()
+    del stack
+    torch.cuda.empty_cache()
+    for D in (1, 60, 360):
+        th = np.deg2rad(np.arange(D) * 360.0 / D)
+        uv = np.stack([0.7 * np.cos(th), 0.7 * np.sin(th)], 1).astype(np.float32)
+        out = torch.empty((D, H, W, 3), dtype=torch.uint8, device="cuda")
+        cb = enc.coef_bytes
+        for _ in range(2):
+            rel.relight_rgb(cb[0], cb[1], cb[2], scale, bias, uv, out)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5 if D < 100 else 2
+        a.record()
+        for _ in range(reps):
+            rel.relight_rgb(cb[0], cb[1], cb[2], scale, bias, uv, out)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        pd = P * D / (ms * 1e-3)
+        bytes_pd = (18 + 3 * D) / D
+        print(json.dumps({"format": "RGB", "directions": D, "ms": ms, "pixel_directions_per_s": pd,
+                          "achieved_GBs": pd * bytes_pd / 1e9, "frac_of_hbm_peak": pd * bytes_pd / 1e9 / peak}))
+        del out
 
 
 if __name__ == "__main__":
