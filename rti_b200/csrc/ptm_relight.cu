@@ -122,6 +122,138 @@ relight_lrgb_x4_kernel(RelightArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// Packed form of the LRGB kernel: the FP32-pipe instructions work on PAIRS of pixels
+// (mul / fma / add.rz .f32x2, SASS FMUL2 / FFMA2 / FADD2.RZ -- IEEE results identical to the scalar
+// instructions; the adds of the polynomial stay scalar, see add2).  A packed instruction occupies the FMA pipe for two cycles but only one issue
+// slot, so the min/max, byte-permute and store instructions of the ALU / LSU pipes issue in its
+// shadow; the scalar kernel is issue bound (tools/ubench_fma.cu measures the overlap).
+// ---------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pk(float lo, float hi) {
+    f32x2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void unpk(f32x2 p, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p));
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// a + b per half with SCALAR adds: ptxas (12.9) contracts mul.rn.f32x2 followed by add.rn.f32x2 into
+// FFMA2 even under --fmad false (it also sees through fma(t, 1, c) and fma(a, b, -0)), which would change
+// the reference's unfused results; a packed multiply feeding scalar adds is left alone (checked in SASS).
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    float a0, a1, b0, b1;
+    unpk(a, a0, a1);
+    unpk(b, b0, b1);
+    return pk(__fadd_rn(a0, b0), __fadd_rn(a1, b1));
+}
+__device__ __forceinline__ f32x2 add2_rz(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+__global__ void __launch_bounds__(kRelightThreads)
+relight_lrgb_x4p_kernel(RelightArgs a) {
+    extern __shared__ __align__(16) float light_s[];  // [n_dirs][12]: (u^2,u^2) (v^2,v^2) (uv,uv) (u,u) (v,v) pad
+    for (unsigned i = threadIdx.x; i < a.n_dirs * 12; i += blockDim.x) {
+        const unsigned d = i / 12, j = (i % 12) >> 1;
+        light_s[i] = j < 5 ? a.light[d * PTM_NCOEF + j] : 0.f;
+    }
+    __syncthreads();
+
+    const size_t pixels = a.width * a.height;
+    const size_t groups = pixels / 4;
+    const size_t gw = a.width / 4;
+    const f32x2 kR = pk(0.003921568859368562698364257812f, 0.003921568859368562698364257812f);  // RN(1 / 255)
+    const f32x2 kM255 = pk(-255.0f, -255.0f);
+    const f32x2 kMagic = pk(8388608.0f, 8388608.0f);
+    for (size_t g = (size_t) blockIdx.x * blockDim.x + threadIdx.x; g < groups;
+         g += (size_t) gridDim.x * blockDim.x) {
+        const size_t y = g / gw, xg = g - y * gw;
+        const size_t p = (a.height - 1 - y) * a.width + xg * 4;
+        const uint2 *c2 = reinterpret_cast<const uint2 *>(a.plane[0] + p * PTM_NCOEF);
+        const uint32_t *r32 = reinterpret_cast<const uint32_t *>(a.plane[1] + p * 3);
+        const uint2 cw[3] = {__ldg(c2), __ldg(c2 + 1), __ldg(c2 + 2)};
+        const uint32_t rw[3] = {__ldg(r32), __ldg(r32 + 1), __ldg(r32 + 2)};
+        const uint32_t cb[6] = {cw[0].x, cw[0].y, cw[1].x, cw[1].y, cw[2].x, cw[2].y};
+        float u[4][PTM_NCOEF], col[4][3];
+        float kb[PTM_NCOEF];
+#pragma unroll
+        for (int k = 0; k < PTM_NCOEF; ++k)
+            kb[k] = 8388608.0f + (float) a.bias[k];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) {
+            const float m = __uint_as_float(__byte_perm(cb[j >> 2], 0x4B000000u, 0x7650u + (j & 3)));
+            u[j / 6][j % 6] = __fmul_rn(a.scale[j % 6], __fsub_rn(m, kb[j % 6]));
+        }
+#pragma unroll
+        for (int j = 0; j < 12; ++j)
+            col[j / 3][j % 3] = byte_to_float(rw[j >> 2], 0x7650u + (j & 3));
+        // pixel pairs (0, 1) and (2, 3)
+        f32x2 U[2][PTM_NCOEF], C[2][3];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int k = 0; k < PTM_NCOEF; ++k)
+                U[h][k] = pk(u[2 * h][k], u[2 * h + 1][k]);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+                C[h][ch] = pk(col[2 * h][ch], col[2 * h + 1][ch]);
+        }
+
+        uint32_t *dst = reinterpret_cast<uint32_t *>(a.out + g * 12);
+        const size_t dir_words = pixels * 3 / 4;
+        for (unsigned d = 0; d < a.n_dirs; ++d) {
+            const ulonglong2 *lp = reinterpret_cast<const ulonglong2 *>(light_s + d * 12);
+            const ulonglong2 l01 = lp[0], l23 = lp[1];
+            const f32x2 l4 = *reinterpret_cast<const f32x2 *>(light_s + d * 12 + 8);
+            unsigned b[12];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                // the reference's association (rti-builder/ptmlib.c:58-63), two pixels per instruction
+                f32x2 s = mul2(U[h][0], l01.x);
+                s = add2(s, mul2(U[h][1], l01.y));
+                s = add2(s, mul2(U[h][2], l23.x));
+                s = add2(s, mul2(U[h][3], l23.y));
+                s = add2(s, mul2(U[h][4], l4));
+                s = add2(s, U[h][5]);
+                // s / 255.0f as in div255(): -q0 * 255 == q0 * -255 exactly
+                const f32x2 q0 = mul2(s, kR);
+                const f32x2 e = fma2(q0, kM255, s);
+                const f32x2 q = fma2(e, kR, q0);
+                float La, Lb;
+                unpk(q, La, Lb);
+                const f32x2 L = pk(fmaxf(La, 0.0f), fmaxf(Lb, 0.0f));
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    float ta, tb;
+                    unpk(mul2(L, C[h][ch]), ta, tb);
+                    float za, zb;
+                    unpk(add2_rz(pk(fminf(ta, 255.0f), fminf(tb, 255.0f)), kMagic), za, zb);
+                    b[(2 * h) * 3 + ch] = __float_as_uint(za);
+                    b[(2 * h + 1) * 3 + ch] = __float_as_uint(zb);
+                }
+            }
+            __stcs(dst + 0, pack4(b[0], b[1], b[2], b[3]));
+            __stcs(dst + 1, pack4(b[4], b[5], b[6], b[7]));
+            __stcs(dst + 2, pack4(b[8], b[9], b[10], b[11]));
+            dst += dir_words;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // RGB formats, 4 consecutive pixels of an output row per thread (width % 4 == 0): three planes of
 // 24 B each, 72 unscaled coefficients in registers, 12 bytes = 3 words out per direction
 // (rti-builder/ptmlib.c:610-619: CLIP(POLY) per channel, both clamps needed).
@@ -168,6 +300,80 @@ relight_rgb_x4_kernel(RelightArgs a) {
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch)
                     b[px * 3 + ch] = clip_bits(poly_eval(u[ch][px], l));
+            __stcs(dst + 0, pack4(b[0], b[1], b[2], b[3]));
+            __stcs(dst + 1, pack4(b[4], b[5], b[6], b[7]));
+            __stcs(dst + 2, pack4(b[8], b[9], b[10], b[11]));
+            dst += dir_words;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// RGB formats, packed form: as relight_rgb_x4_kernel with the multiplies and the truncating add on
+// pixel pairs.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRelightThreads, 2)
+relight_rgb_x4p_kernel(RelightArgs a) {
+    extern __shared__ __align__(16) float light_s[];  // [n_dirs][12]: (u^2,u^2) (v^2,v^2) (uv,uv) (u,u) (v,v) pad
+    for (unsigned i = threadIdx.x; i < a.n_dirs * 12; i += blockDim.x) {
+        const unsigned d = i / 12, j = (i % 12) >> 1;
+        light_s[i] = j < 5 ? a.light[d * PTM_NCOEF + j] : 0.f;
+    }
+    __syncthreads();
+
+    const size_t pixels = a.width * a.height;
+    const size_t groups = pixels / 4;
+    const size_t gw = a.width / 4;
+    const f32x2 kMagic = pk(8388608.0f, 8388608.0f);
+    float kb[PTM_NCOEF];
+#pragma unroll
+    for (int k = 0; k < PTM_NCOEF; ++k)
+        kb[k] = 8388608.0f + (float) a.bias[k];
+    for (size_t g = (size_t) blockIdx.x * blockDim.x + threadIdx.x; g < groups;
+         g += (size_t) gridDim.x * blockDim.x) {
+        const size_t y = g / gw, xg = g - y * gw;
+        const size_t p = (a.height - 1 - y) * a.width + xg * 4;
+        f32x2 U[3][2][PTM_NCOEF];   // [channel][pixel pair][coefficient]
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const uint2 *c2 = reinterpret_cast<const uint2 *>(a.plane[ch] + p * PTM_NCOEF);
+            const uint2 cw[3] = {__ldg(c2), __ldg(c2 + 1), __ldg(c2 + 2)};
+            const uint32_t cb[6] = {cw[0].x, cw[0].y, cw[1].x, cw[1].y, cw[2].x, cw[2].y};
+            float u[4][PTM_NCOEF];
+#pragma unroll
+            for (int j = 0; j < 24; ++j) {
+                const float m = __uint_as_float(__byte_perm(cb[j >> 2], 0x4B000000u, 0x7650u + (j & 3)));
+                u[j / 6][j % 6] = __fmul_rn(a.scale[j % 6], __fsub_rn(m, kb[j % 6]));
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int k = 0; k < PTM_NCOEF; ++k)
+                    U[ch][h][k] = pk(u[2 * h][k], u[2 * h + 1][k]);
+        }
+        uint32_t *dst = reinterpret_cast<uint32_t *>(a.out + g * 12);
+        const size_t dir_words = pixels * 3 / 4;
+        for (unsigned d = 0; d < a.n_dirs; ++d) {
+            const ulonglong2 *lp = reinterpret_cast<const ulonglong2 *>(light_s + d * 12);
+            const ulonglong2 l01 = lp[0], l23 = lp[1];
+            const f32x2 l4 = *reinterpret_cast<const f32x2 *>(light_s + d * 12 + 8);
+            unsigned b[12];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    f32x2 s = mul2(U[ch][h][0], l01.x);
+                    s = add2(s, mul2(U[ch][h][1], l01.y));
+                    s = add2(s, mul2(U[ch][h][2], l23.x));
+                    s = add2(s, mul2(U[ch][h][3], l23.y));
+                    s = add2(s, mul2(U[ch][h][4], l4));
+                    s = add2(s, U[ch][h][5]);
+                    float ta, tb, za, zb;
+                    unpk(s, ta, tb);
+                    unpk(add2_rz(pk(fminf(fmaxf(ta, 0.0f), 255.0f), fminf(fmaxf(tb, 0.0f), 255.0f)), kMagic), za, zb);
+                    b[(2 * h) * 3 + ch] = __float_as_uint(za);
+                    b[(2 * h + 1) * 3 + ch] = __float_as_uint(zb);
+                }
             __stcs(dst + 0, pack4(b[0], b[1], b[2], b[3]));
             __stcs(dst + 1, pack4(b[4], b[5], b[6], b[7]));
             __stcs(dst + 2, pack4(b[8], b[9], b[10], b[11]));
@@ -261,7 +467,15 @@ cudaError_t launch_relight(const RelightArgs &a, bool lrgb, int sm_count, cudaSt
         size_t want = (pixels / 4 + kRelightThreads - 1) / kRelightThreads;
         size_t cap = (size_t) sm_count * 8;
         unsigned grid = (unsigned) (want < cap ? want : cap);
-        relight_lrgb_x4_kernel<<<grid, kRelightThreads, (size_t) a.n_dirs * 8 * sizeof(float), st>>>(a);
+        static int packed = -1;
+        if (packed < 0) {
+            const char *v = getenv("PTM_RELIGHT_PACKED");   // tuning aid: 0 = scalar FP32 instructions
+            packed = v ? atoi(v) : 1;
+        }
+        if (packed && a.n_dirs >= 4)   // a single direction is memory bound: the scalar kernel has less set-up
+            relight_lrgb_x4p_kernel<<<grid, kRelightThreads, (size_t) a.n_dirs * 12 * sizeof(float), st>>>(a);
+        else
+            relight_lrgb_x4_kernel<<<grid, kRelightThreads, (size_t) a.n_dirs * 8 * sizeof(float), st>>>(a);
         return cudaGetLastError();
     }
     static int x4_rgb = -1;
@@ -276,7 +490,15 @@ cudaError_t launch_relight(const RelightArgs &a, bool lrgb, int sm_count, cudaSt
         size_t want4 = (pixels / 4 + kRelightThreads - 1) / kRelightThreads;
         size_t cap4 = (size_t) sm_count * 2;
         unsigned grid4 = (unsigned) (want4 < cap4 ? want4 : cap4);
-        relight_rgb_x4_kernel<<<grid4, kRelightThreads, (size_t) a.n_dirs * 8 * sizeof(float), st>>>(a);
+        static int packed3 = -1;
+        if (packed3 < 0) {
+            const char *v = getenv("PTM_RELIGHT_PACKED");
+            packed3 = v ? atoi(v) : 1;
+        }
+        if (packed3 && a.n_dirs >= 4)
+            relight_rgb_x4p_kernel<<<grid4, kRelightThreads, (size_t) a.n_dirs * 12 * sizeof(float), st>>>(a);
+        else
+            relight_rgb_x4_kernel<<<grid4, kRelightThreads, (size_t) a.n_dirs * 8 * sizeof(float), st>>>(a);
         return cudaGetLastError();
     }
     size_t want = (pixels + kRelightThreads - 1) / kRelightThreads;

@@ -282,6 +282,27 @@ def test_relight_matches_oracle_exactly(ctx, oracle, dome1, M60):
                                                                   float(u), float(v)))
 
 
+def test_relight_rgb_format_matches_oracle_exactly(ctx, oracle, dome1, M60):
+    """RGB-format PTMs (three coefficient planes, CLIP(POLY) per channel, rti-builder/ptmlib.c:610-619):
+    the packed 4-pixel kernel (>= 4 directions), the scalar 4-pixel kernel (fewer) and the generic kernel
+    (odd width) are all bit-exact against the restated loop."""
+    rng = np.random.default_rng(9)
+    for W, H in ((52, 35), (37, 9)):
+        stack = oracle.synth_stack(23, 1, W, H, dome1)
+        enc = oracle.encode_rgb(stack, M60)
+        scale = oracle.header_roundtrip(enc["scale"])
+        uv = np.concatenate([[[0, 0], [0.5, 0.5], [1, 0], [0, -1]],
+                             rng.uniform(-0.9, 0.9, size=(9, 2))]).astype(np.float32)
+        planes = [dev(enc["coef"][c]) for c in range(3)]
+        for nd in (len(uv), 2):
+            out = torch.empty((nd, H, W, 3), dtype=torch.uint8, device="cuda")
+            ctx.relight_rgb(planes[0], planes[1], planes[2], W, H, scale, enc["bias"], uv[:nd], out)
+            got = out.cpu().numpy()
+            for i in range(nd):
+                np.testing.assert_array_equal(got[i], oracle.relight_rgb(enc["coef"], scale, enc["bias"],
+                                                                         float(uv[i, 0]), float(uv[i, 1])))
+
+
 def test_clip_edge_values(ctx):
     """CLIP (rti-builder/ptmlib.h:156-158) at its edges through K2: extrema 0 and 256 give
     scale 1, bias 0, so bytes are clip(trunc(c))."""
