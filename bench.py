@@ -342,7 +342,7 @@ def run_b200(args):
                    "rows_per_gpu": rows, "l2": "inputs larger than L2 (%.0f MB stack per GPU, streamed once per step)"
                                                % (stack.numel() / 1e6),
                    "exchange": {"none": "none", "nccl": "int32 MAX all-reduce of 12 keys (NCCL)",
-                                "p2p": "12 int32 keys through NVLink peer-memory mailboxes (2 one-block kernels)"}
+                                "p2p": "12 int32 keys written into every peer's mailbox over NVLink by K1's last block, picked up in K2's prologue"}
                                [enc.exchange_kind]},
         "roofline": {"bound": "hbm", "kernel": "fit_lrgb_u8 (K1)", "achieved": k1_gbs, "peak": peak, "unit": "GB/s",
                      "frac": k1_gbs / peak, "traffic": traffic, "peak_source": peak_src,
