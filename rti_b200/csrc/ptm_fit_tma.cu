@@ -116,6 +116,10 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
     float4 *m_s = reinterpret_cast<float4 *>(smem + Smem::matrix);
 
     const unsigned n = a.n_lights;
+    // In the fused encode this kernel is itself launched programmatically dependent on the previous
+    // K2 (its blocks become resident while K2's last blocks drain): nothing is read or written before
+    // that grid has completed.  A no-op for an ordinary launch.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // a programmatically dependent K2 (the fused encode) may be scheduled as soon as SM resources free up
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) {
@@ -305,6 +309,20 @@ static cudaError_t launch_variant(const FitArgs &a, size_t n_tiles, unsigned tai
     size_t grid = (size_t) sm_count * per_sm_cache[dev][slot];
     if (grid > n_tiles)
         grid = n_tiles;
+    if (a.handoff.ticket) {
+        // fused encode: K1 -> K2 -> K1 -> ... each launched programmatically dependent on its predecessor
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned) grid);
+        cfg.blockDim = dim3(kTmaThreads);
+        cfg.dynamicSmemBytes = Smem::total(a.n_lights);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kern, a, (unsigned) n_tiles, tail_px);
+    }
     kern<<<(unsigned) grid, kTmaThreads, Smem::total(a.n_lights), st>>>(a, (unsigned) n_tiles, tail_px);
     return cudaGetLastError();
 }

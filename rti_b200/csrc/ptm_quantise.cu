@@ -25,6 +25,9 @@ quantise_kernel(const float *__restrict__ coeffs, size_t n_float4, size_t tail_f
     __shared__ float bias_s[PTM_NCOEF];
     __shared__ int keys[2 * PTM_NCOEF];
     keys_fetch<KeySource, XchgLayout>(ksrc, keys, kMaxRanks, kSlotInts);
+    // the next fit of a fused encode loop may start occupying SMs as this grid drains (it waits for
+    // this grid's completion before touching memory, see fit_lrgb_u8_tma_kernel)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x < PTM_NCOEF) {
         float scale, inv;
         int bias;
