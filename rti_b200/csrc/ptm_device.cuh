@@ -225,7 +225,11 @@ __device__ __forceinline__ void scale_bias_from_keys(const int *keys, int k, flo
     const float mx = key_to_float(keys[PTM_NCOEF + k]);
     const float range = __fsub_rn(mx, mn);
     scale = __fdiv_rn(range, 256.0f);
-    bias = (int) __fmul_rn(__fdiv_rn(-256.0f, range), mn);
+    // (int) of a NaN or out-of-range float is undefined in C; the reference runs on x86, where the
+    // conversion (cvttss2si) then yields INT_MIN -- e.g. for a constant image (range == 0).  CUDA's
+    // conversion would saturate / return 0 instead, so the x86 result is spelled out.
+    const float fb = __fmul_rn(__fdiv_rn(-256.0f, range), mn);
+    bias = (fb >= -2147483648.0f && fb < 2147483648.0f) ? (int) fb : (int) 0x80000000;
     inv = __fdiv_rn(1.0f, scale);
 }
 

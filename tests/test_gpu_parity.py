@@ -116,6 +116,44 @@ def test_lrgb_encode_vs_oracle(ctx, oracle, dome1, M60, W, H, seed):
             assert_bytes_close(got["coef"], want["coef"], "LRGB coefficient bytes %dx%d" % (W, H), 0.02)
 
 
+def test_degenerate_inputs_follow_the_reference(ctx, oracle, dome1, M60):
+    """Inputs the reference does not guard against (rti-builder/ptm-encoder.c:342 divides by the mean luma,
+    rti-builder/ptmlib.c:860-862 by the coefficient range): a pixel that is black in every image gets NaN
+    coefficients, which fminf/fmaxf skip and CLIP turns into byte 0; a constant stack has range 0, scale 0
+    and the x86 float->int result INT_MIN as bias.  The GPU path reproduces both."""
+    W, H = 32, 8
+    stack = oracle.synth_stack(77, 0, W, H, dome1)
+    stack[:, 3, 5, :] = 0          # black in every light
+    stack[:, 4, 6, 0] = 0          # zero luma, chroma kept
+    want = oracle.encode_lrgb(stack, M60)
+    for engine in ("ffma", "mma"):
+        ctx.set_fit_engine(engine)
+        got = gpu_encode_lrgb(ctx, stack, M60)
+        np.testing.assert_array_equal(got["rgb"], want["rgb"])
+        assert np.isnan(got["coeffs"][3, 5]).all() and np.isnan(got["coeffs"][4, 6]).all()
+        assert np.array_equal(np.isnan(got["coeffs"]), np.isnan(want["coeffs"]))
+        # 256 pixels: the range is a few hundred ulps of the extrema, which carry the oracle's summation noise
+        np.testing.assert_allclose(got["scale"], want["scale"], rtol=5e-6)
+        assert np.abs(got["bias"].astype(np.int64) - want["bias"].astype(np.int64)).max() <= 1
+        assert (got["coef"][3, 5] == 0).all() and (got["coef"][4, 6] == 0).all()
+        if np.array_equal(got["bias"], want["bias"]):
+            assert_bytes_close(got["coef"], want["coef"], "bytes with NaN pixels (%s)" % engine, 0.02)
+    ctx.set_fit_engine("default")
+    flat = np.full((60, H, W, 3), 128, dtype=np.uint8)
+    flat[..., 0] = 100
+    want = oracle.encode_lrgb(flat, M60)
+    got = gpu_encode_lrgb(ctx, flat, M60)
+    np.testing.assert_array_equal(got["rgb"], want["rgb"])
+    # every pixel has the same coefficients whatever the summation order, so the range is exactly 0
+    assert (got["scale"] == 0).all() and (want["scale"] == 0).all()
+    np.testing.assert_array_equal(got["bias"], want["bias"])
+    assert (got["bias"] == -2**31).all()
+    # byte = CLIP(c * inf + bias): 255 for positive coefficients, 0 for negative ones; a coefficient whose
+    # float sum cancels to +-0 or to rounding noise may differ in sign between summation orders
+    sure = np.abs(want["coeffs"]) > 1e-3
+    np.testing.assert_array_equal(got["coef"][sure], want["coef"][sure])
+
+
 def test_lrgb_quantise_is_exact_given_same_floats(ctx, oracle, dome1, M60):
     """K2 alone: fed the ORACLE's float coefficients, bytes, scale and bias are identical."""
     stack = oracle.synth_stack(11, 0, 96, 50, dome1)
