@@ -654,10 +654,9 @@ int ptmb_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, int sample_type,
         const size_t rows = height - row < slab_rows ? height - row : slab_rows;
         const size_t px0 = row * width, npx = rows * width;
         CK(cudaStreamWaitEvent(s.copy, s.consumed[buf], 0));
-        for (unsigned n = 0; n < n_lights; ++n)
-            CK(cudaMemcpyAsync((uint8_t *) s.stage[buf] + n * slab_stride,
-                               (const uint8_t *) stack_host + n * image_bytes + px0 * 3 * ss, npx * 3 * ss,
-                               cudaMemcpyHostToDevice, s.copy));
+        // one strided copy per slab: n_lights rows of npx * 3 * ss bytes, host pitch = one image
+        CK(cudaMemcpy2DAsync(s.stage[buf], slab_stride, (const uint8_t *) stack_host + px0 * 3 * ss, image_bytes,
+                             npx * 3 * ss, n_lights, cudaMemcpyHostToDevice, s.copy));
         CK(cudaEventRecord(s.copied[buf], s.copy));
         CK(cudaStreamWaitEvent(c->stream, s.copied[buf], 0));
         ptm::FitArgs a;

@@ -181,7 +181,7 @@ __device__ __forceinline__ long long digits_to_int(const int *d) {
 }  // namespace
 
 // kMode: 0 = RGB formats, uint8; 1 = LRGB, uint8; 2 = RGB formats, uint16; 3 = LRGB, uint16
-// kDebug (tuning builds, never the default): 1 = epilogue only drains TMEM (load + MMA ceiling),
+// kDebug (only instantiated in -DPTM_TUNING builds): 1 = epilogue only drains TMEM (load + MMA ceiling),
 // 2 = additionally no MMAs are issued (TMA delivery ceiling), 3 = MMAs and drain but no loads (MMA ceiling)
 template <int kMode, int G, int kDebug = 0>
 __global__ void __launch_bounds__(64 + 128 * G, 1)
@@ -753,9 +753,11 @@ cudaError_t launch_fit_mma(const FitArgs &a, int mode, int sm_count, cudaStream_
         e = mode == 0 ? launch_mode<0, 4>(maps, a, m, smem, grid, st)
             : mode == 1 ? launch_mode<1, 4>(maps, a, m, smem, grid, st) : launch_mode<2, 4>(maps, a, m, smem, grid, st);
         break;
+#ifdef PTM_TUNING   // ceilings only: these variants skip work and do NOT produce results (make EXTRA_NVFLAGS=-DPTM_TUNING)
     case 2: e = mode == 2 ? launch_mode<2, 2, 1>(maps, a, m, smem, grid, st) : launch_mode<1, 2, 1>(maps, a, m, smem, grid, st); break;
     case 3: e = mode == 2 ? launch_mode<2, 2, 2>(maps, a, m, smem, grid, st) : launch_mode<1, 2, 2>(maps, a, m, smem, grid, st); break;
     case 4: e = mode == 2 ? launch_mode<2, 2, 3>(maps, a, m, smem, grid, st) : launch_mode<1, 2, 3>(maps, a, m, smem, grid, st); break;
+#endif
     default:
         e = mode == 0 ? launch_mode<0, 2>(maps, a, m, smem, grid, st)
             : mode == 1 ? launch_mode<1, 2>(maps, a, m, smem, grid, st) : launch_mode<2, 2>(maps, a, m, smem, grid, st);

@@ -97,7 +97,7 @@ __device__ __forceinline__ void sum_pair(const uint32_t *a, const uint32_t *b, u
     }
 }
 
-// kDebug (tuning builds only, never selected by default): 1 = consumers skip the arithmetic
+// kDebug (only instantiated in -DPTM_TUNING builds): 1 = consumers skip the arithmetic
 // (ring delivery ceiling), 2 = consumers skip the waits (arithmetic ceiling).
 // kFull: the light count is a multiple of L, so every stage is complete (no per-stage count).
 __device__ __forceinline__ unsigned tile_px_of(unsigned tile, unsigned n_tiles, unsigned tail_px) {
@@ -570,7 +570,9 @@ cudaError_t launch_fit_lrgb_tma(const FitArgs &a, int sm_count, cudaStream_t st,
     case 3: e = launch_variant<5, 4>(a, n_tiles, tail_px, sm_count, st); break;
     case 4: e = launch_variant<4, 5>(a, n_tiles, tail_px, sm_count, st); break;
     case 5: e = launch_variant<8, 3>(a, n_tiles, tail_px, sm_count, st); break;
+#ifdef PTM_TUNING   // delivery ceiling only: skips the arithmetic, does NOT produce results
     case 11: e = launch_variant<6, 4, 1>(a, n_tiles, tail_px, sm_count, st); break;
+#endif
     default: e = launch_variant<6, 4>(a, n_tiles, tail_px, sm_count, st); break;
     }
     if (e == cudaSuccess)

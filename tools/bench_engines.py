@@ -1,6 +1,10 @@
 #!/usr/bin/env python
 """FFMA engine against the tensor-core engine on the same resident stack: fit alone (K1) and the
-whole encode, LRGB and RGB formats, uint8, 24 MP x dome1.lp by default.  One JSON line per case."""
+whole encode, LRGB and RGB formats, uint8, 24 MP x dome1.lp by default.  One JSON line per case.
+
+Tuning: PTM_MMA_VARIANT=1 runs four epilogue groups; variants 2-4 (ceilings: load + MMA only, TMA
+delivery only, MMA only) exist only in a library built with `make EXTRA_NVFLAGS=-DPTM_TUNING` and do
+not produce results.  PTM_MMA_SCHED=0 strides units over the grid, PTM_MMA_LOAD=0 uses plain 2-D boxes."""
 import json
 import os
 import sys
