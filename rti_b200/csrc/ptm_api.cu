@@ -75,9 +75,9 @@ int ptmb_create(int device, void *stream, ptmb_ctx_t **out) {
     if (e == cudaSuccess)
         e = cudaMalloc(&c->sb_dev, sizeof(ptmb_scale_bias_t));
     if (e == cudaSuccess)
-        e = cudaMalloc(&c->ticket_dev, sizeof(unsigned));
+        e = cudaMalloc(&c->ticket_dev, 2 * sizeof(unsigned));   // [0] ticket, [1] dynamic tile counter
     if (e == cudaSuccess)
-        e = cudaMemset(c->ticket_dev, 0, sizeof(unsigned));
+        e = cudaMemset(c->ticket_dev, 0, 2 * sizeof(unsigned));
     if (e == cudaSuccess)
         e = cudaMalloc(&c->mailbox_dev, ptm::XchgLayout::bytes);
     if (e == cudaSuccess)
@@ -253,6 +253,7 @@ static int make_fit_args(ptmb_ctx_t *c, const void *stack_dev, size_t image_stri
     memcpy(a.digit_scale, c->digit_scale, sizeof(a.digit_scale));
     a.kpad = c->kpad;
     a.engine = c->engine;
+    a.tile_counter = c->ticket_dev ? c->ticket_dev + 1 : nullptr;
     return 0;
 }
 
@@ -377,6 +378,7 @@ int ptmb_encode_lrgb_dev(ptmb_ctx_t *c, ptmb_xchg_t *x, const void *stack_dev, i
     size_t done = 0;
     if (sample_type == PTMB_U8 && pixels > 0) {
         a.handoff.ticket = c->ticket_dev;
+        a.handoff.tile_counter = a.tile_counter;
         a.handoff.world = x ? x->world : 1;
         a.handoff.rank = x ? x->rank : 0;
         a.handoff.epoch = x ? x->epoch + 1 : c->epoch + 1;

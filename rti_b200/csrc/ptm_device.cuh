@@ -143,8 +143,11 @@ __device__ __forceinline__ void keys_handoff(const Handoff &h, int *keys, int ma
             slots[(parity * max_ranks + h.rank) * slot_ints + threadIdx.x] = v;
         }
     }
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
         *h.ticket = 0;   // before the flags: once they are up the next fit may be on its way
+        if (h.tile_counter)
+            *h.tile_counter = 0;   // every block has stopped drawing tiles before it took its ticket
+    }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x < h.world) {

@@ -104,12 +104,32 @@ __device__ __forceinline__ unsigned tile_px_of(unsigned tile, unsigned n_tiles, 
     return (tail_px && tile + 1 == n_tiles) ? tail_px : (unsigned) kTilePx;
 }
 
+#ifdef PTM_TUNING
+// per-CTA timeline of the last launch: entry, first stage consumed, last tile stored, exit (globaltimer ns)
+__device__ unsigned long long g_cta_times[4 * 1024];
+__device__ __forceinline__ void cta_stamp(int slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (blockIdx.x < 1024)
+        g_cta_times[4 * blockIdx.x + slot] = t;
+}
+#define PTM_STAMP(slot) cta_stamp(slot)
+#else
+#define PTM_STAMP(slot)
+#endif
+
 template <int L, int S, bool kWriteCoeffs, bool kFull, int kDebug = 0>
 __global__ void __launch_bounds__(kTmaThreads, 2)
 fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
     using Smem = TmaSmem<L, S>;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ int keys_s[2 * PTM_NCOEF];
+    // Tile schedule.  The first tile of a block is blockIdx.x; with a.tile_counter the following ones are
+    // drawn from a device-wide counter by the producer (blocks on faster SMs take more tiles: the spread
+    // between the first and the last block to finish was 10 % of the kernel with a static stride) and
+    // announced to the consumers through tile_pub[tile parity], published by the mbarrier arrive of the
+    // tile's first stage.  A tile index >= n_tiles tells the consumers to stop.
+    __shared__ unsigned tile_pub[2];
     uint8_t *ring = smem;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + Smem::bars);
     uint64_t *empty = full + S;
@@ -120,6 +140,8 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
     // K2 (its blocks become resident while K2's last blocks drain): nothing is read or written before
     // that grid has completed.  A no-op for an ordinary launch.
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0)
+        PTM_STAMP(0);
     // a programmatically dependent K2 (the fused encode) may be scheduled as soon as SM resources free up
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) {
@@ -150,8 +172,25 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
         // ------------------------------------------------------------ producer
         // lane 0 owns the barrier protocol; lanes 0..L-1 each issue one light's copy of the stage
         const uint64_t policy = l2_policy_evict_first();
-        unsigned s = 0, ph = 0;
-        for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        unsigned s = 0, ph = 0, slot = 0;
+        unsigned tile = blockIdx.x;
+        for (;;) {
+            if (lane == 0) {
+                mbar_wait(&empty[s], ph ^ 1);          // also orders this write after the readers of the slot
+                tile_pub[slot] = tile;
+            }
+            if (tile >= n_tiles) {
+                if (lane == 0)
+                    mbar_arrive(&full[s]);             // wake the consumers: nothing more to do
+                break;
+            }
+            // draw the next tile now, its latency hides behind this tile's copies
+            unsigned next = tile + gridDim.x;
+            if (a.tile_counter) {
+                if (lane == 0)
+                    next = gridDim.x + atomicAdd(a.tile_counter, 1u);
+                next = __shfl_sync(0xFFFFFFFFu, next, 0);
+            }
             const uint8_t *src = a.stack + (size_t) tile * kTileBytes + (size_t) lane * a.image_stride;
             // the last tile may be partial (tail_px pixels, a multiple of 16 => bytes a multiple of 16)
             const unsigned bytes = (tail_px && tile + 1 == n_tiles) ? tail_px * 3 : (unsigned) kTileBytes;
@@ -159,7 +198,8 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
                 const unsigned l0 = c * L;
                 const unsigned cnt = kFull ? (unsigned) L : min((unsigned) L, n - l0);
                 if (lane == 0) {
-                    mbar_wait(&empty[s], ph ^ 1);
+                    if (c != 0)
+                        mbar_wait(&empty[s], ph ^ 1);
                     mbar_arrive_expect_tx(&full[s], cnt * bytes);
                 }
                 __syncwarp();
@@ -171,12 +211,15 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
                     ph ^= 1;
                 }
             }
+            tile = next;
+            slot ^= 1;
         }
     } else {
         // ----------------------------------------------------------- consumers
         const unsigned t = threadIdx.x;  // 0..255, owns pixels 4t..4t+3 of the tile
-        unsigned s = 0, ph = 0;
-        for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        unsigned s = 0, ph = 0, slot = 0;
+        for (bool first = true;; first = false, slot ^= 1) {
+            unsigned tile = 0;
             float acc[4][PTM_NCOEF];
 #pragma unroll
             for (int p = 0; p < 4; ++p)
@@ -185,9 +228,18 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
                     acc[p][k] = 0.f;
             unsigned ev[3] = {0, 0, 0}, od[3] = {0, 0, 0};
 
+            bool stop = false;
             for (unsigned c = 0; c < n_chunks; ++c) {
-                if (kDebug != 2)
-                    mbar_wait(&full[s], ph);
+                mbar_wait(&full[s], ph);
+                if (c == 0) {
+                    tile = *reinterpret_cast<volatile unsigned *>(&tile_pub[slot]);
+                    if (tile >= n_tiles) {
+                        stop = true;
+                        break;
+                    }
+                }
+                if (threadIdx.x == 0 && first && c == 0)
+                    PTM_STAMP(1);
                 const uint32_t *buf = reinterpret_cast<const uint32_t *>(ring + (size_t) s * Smem::stage_bytes) + 3 * t;
                 const unsigned l0 = c * L;
                 const unsigned cnt = kFull ? (unsigned) L : min((unsigned) L, n - l0);
@@ -216,6 +268,8 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
                 }
             }
 
+            if (stop)
+                break;
             // per-byte sums: odd bytes from the 16-bit lanes, even bytes from the plain word sum
             unsigned sum[12];
 #pragma unroll
@@ -272,10 +326,20 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
             __syncwarp();
         }
     }
+    if (threadIdx.x == 0)
+        PTM_STAMP(2);
     ext.flush(a.keys, keys_s);
     if (a.handoff.ticket)
         keys_handoff<KeyHandoff, XchgLayout>(a.handoff, a.keys, kMaxRanks, kSlotInts);
+    if (threadIdx.x == 0)
+        PTM_STAMP(3);
 }
+
+#ifdef PTM_TUNING
+extern "C" int ptmb_tuning_cta_times(unsigned long long *out, int n) {
+    return (int) cudaMemcpyFromSymbol(out, g_cta_times, sizeof(unsigned long long) * (size_t) n);
+}
+#endif
 
 template <int L, int S, int kDebug = 0>
 static cudaError_t launch_variant(const FitArgs &a, size_t n_tiles, unsigned tail_px, int sm_count, cudaStream_t st) {
@@ -309,6 +373,12 @@ static cudaError_t launch_variant(const FitArgs &a, size_t n_tiles, unsigned tai
     size_t grid = (size_t) sm_count * per_sm_cache[dev][slot];
     if (grid > n_tiles)
         grid = n_tiles;
+    if (a.tile_counter && !a.handoff.ticket) {
+        // no hand-off block to reset the tile counter after the launch: clear it in stream order before
+        e = cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned), st);
+        if (e != cudaSuccess)
+            return e;
+    }
     if (a.handoff.ticket) {
         // fused encode: K1 -> K2 -> K1 -> ... each launched programmatically dependent on its predecessor
         cudaLaunchConfig_t cfg = {};

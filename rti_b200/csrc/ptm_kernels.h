@@ -25,6 +25,7 @@ struct XchgLayout {
 // every rank (its own included) under `epoch`, and reset keys + ticket for the next launch.
 struct KeyHandoff {
     unsigned *ticket;           // device counter, 0 between launches; nullptr = no hand-off
+    unsigned *tile_counter;     // K1's dynamic tile counter, reset by the last block (may be nullptr)
     int *mailbox[kMaxRanks];
     int world, rank;
     unsigned epoch;
@@ -54,6 +55,7 @@ struct FitArgs {
     const int8_t *digits;   // nullptr = not available for this matrix
     float digit_scale[6];   // 2^-F_k
     unsigned kpad;          // lights rounded up to 32
+    unsigned *tile_counter; // dynamic tile scheduling of the LRGB ring kernel: device counter, 0 at launch (nullptr = static)
     int engine;             // PTMB_ENGINE_*: 0 = default choice, 1 = FFMA kernels, 2 = tensor-core kernel
 };
 
