@@ -77,7 +77,8 @@ struct MmaArgs {
     unsigned tail_px;         // pixels of the last unit when it is partial, else 0
     unsigned row_bytes;       // bytes of one image that the units cover
     unsigned grouped;         // 1: whole units are loaded light-group-major (see the producer)
-    unsigned chunk;           // units per CTA when CTAs own consecutive units, 0 = units strided by the grid
+    unsigned run_units;       // units per run: a CTA draws runs of consecutive units (DRAM row locality inside a run)
+    unsigned *counter;        // device-wide run counter, 0 at launch (nullptr: runs strided by the grid)
 };
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
@@ -241,42 +242,70 @@ fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     Extrema ext;
     ext.init();
 
-    // which units this CTA owns: strided by the grid, or one run of consecutive units (the ring then holds
-    // several adjacent 384-byte pieces of every light: more DRAM row hits)
-    const unsigned u_first = m.chunk ? blockIdx.x * m.chunk : blockIdx.x;
-    const unsigned u_last = m.chunk ? min(m.n_units, u_first + m.chunk) : m.n_units;
-    const unsigned u_step = m.chunk ? 1u : gridDim.x;
+    // Schedule: a CTA works on RUNS of consecutive units (the ring then holds several adjacent 384-byte pieces
+    // of every light: more DRAM row hits).  Its first run is blockIdx.x, the following ones are drawn from a
+    // device-wide counter by the producer (CTAs on faster SMs take more; with a fixed split the slowest CTA set
+    // the kernel time).  The producer announces each unit through unit_pub[local index % 32] before it arms
+    // the stage's barrier; kNoUnit tells the MMA warp and, through it, every epilogue group to stop.
+    __shared__ unsigned unit_pub[32];
+    constexpr unsigned kNoUnit = 0xFFFFFFFFu;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         // (the whole warp runs the loop converged; one elected lane issues)
         const uint64_t policy = l2_policy_evict_first();
         const unsigned groups = a.n_lights / 8, rem = a.n_lights % 8;
-        unsigned s = 0, ph = 0;
-        for (unsigned u = u_first; u < u_last; u += u_step) {
-            const unsigned byte0 = u * kUnitBytes;
-            const unsigned left = m.row_bytes - byte0;
-            const unsigned nblk = left >= (unsigned) kUnitBytes ? kUnitBlocks : (left + kBlk - 1) / kBlk;
-            mbar_wait(&empty[s], ph ^ 1);
-            uint8_t *dst = ring + (size_t) s * stage_bytes;
-            if (elect_one()) {
-                if (kDebug == 3) {
-                    mbar_arrive(&full[s]);
-                } else if (m.grouped && left >= (unsigned) kUnitBytes) {
-                    // Whole unit, light-group-major: one box = [8-light group][column block][8 lights][128 B],
-                    // so the three 128-byte pieces of a light are requested 8 pieces apart (DRAM row hits)
-                    // instead of a whole light set apart.  Stage layout [group][block][8 x 128 B swizzle atom].
-                    mbar_arrive_expect_tx(&full[s], (groups + (rem ? 1 : 0)) * (kUnitBytes * 8));
-                    if (groups)
-                        tma_load_4d(dst, &tmap_grp, 0, 0, (int) (u * kUnitBlocks), 0, &full[s], policy);
-                    if (rem)
-                        tma_load_3d(dst + (size_t) groups * (kUnitBytes * 8), &tmap_rem, 0, 0, (int) (u * kUnitBlocks),
-                                    &full[s], policy);
-                } else {
-                    mbar_arrive_expect_tx(&full[s], nblk * kBlk * a.n_lights);
-                    for (unsigned c = 0; c < nblk; ++c)
-                        tma_load_2d(dst + (size_t) c * blk_bytes, &tmap, (int) (byte0 + c * kBlk), 0, &full[s], policy);
+        unsigned s = 0, ph = 0, i = 0;
+        unsigned run = blockIdx.x;
+        while ((size_t) run * m.run_units < m.n_units) {
+            unsigned next = run + gridDim.x;
+            if (m.counter) {   // draw the next run now: the atomic's latency hides behind this run's copies
+                if (lane == 0)
+                    next = gridDim.x + atomicAdd(m.counter, 1u);
+                next = __shfl_sync(0xFFFFFFFFu, next, 0);
+            }
+            const unsigned u0 = run * m.run_units, u1 = min(m.n_units, u0 + m.run_units);
+            for (unsigned u = u0; u < u1; ++u, ++i) {
+                const unsigned byte0 = u * kUnitBytes;
+                const unsigned left = m.row_bytes - byte0;
+                const unsigned nblk = left >= (unsigned) kUnitBytes ? kUnitBlocks : (left + kBlk - 1) / kBlk;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t *dst = ring + (size_t) s * stage_bytes;
+                if (elect_one()) {
+                    unit_pub[i & 31] = u;
+                    if (kDebug == 3) {
+                        mbar_arrive(&full[s]);
+                    } else if (m.grouped && left >= (unsigned) kUnitBytes) {
+                        // Whole unit, light-group-major: one box = [8-light group][column block][8 lights][128 B],
+                        // so the three 128-byte pieces of a light are requested 8 pieces apart (DRAM row hits)
+                        // instead of a whole light set apart.  Stage layout [group][block][8 x 128 B swizzle atom].
+                        mbar_arrive_expect_tx(&full[s], (groups + (rem ? 1 : 0)) * (kUnitBytes * 8));
+                        if (groups)
+                            tma_load_4d(dst, &tmap_grp, 0, 0, (int) (u * kUnitBlocks), 0, &full[s], policy);
+                        if (rem)
+                            tma_load_3d(dst + (size_t) groups * (kUnitBytes * 8), &tmap_rem, 0, 0,
+                                        (int) (u * kUnitBlocks), &full[s], policy);
+                    } else {
+                        mbar_arrive_expect_tx(&full[s], nblk * kBlk * a.n_lights);
+                        for (unsigned c = 0; c < nblk; ++c)
+                            tma_load_2d(dst + (size_t) c * blk_bytes, &tmap, (int) (byte0 + c * kBlk), 0, &full[s],
+                                        policy);
+                    }
                 }
+                __syncwarp();
+                if (++s == m.stages) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+            run = next;
+        }
+        // one stop mark per epilogue group
+        for (int e = 0; e < G; ++e, ++i) {
+            mbar_wait(&empty[s], ph ^ 1);
+            if (elect_one()) {
+                unit_pub[i & 31] = kNoUnit;
+                mbar_arrive(&full[s]);
             }
             __syncwarp();
             if (++s == m.stages) {
@@ -290,14 +319,27 @@ fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         const uint32_t ring_a = smem_addr(ring);
         const unsigned ksteps = m.kpad / 32;
         const uint64_t bdesc0 = smem_desc(smem_addr(bdig), 512, 128, 0);
-        unsigned s = 0, ph = 0, i = 0;
-        for (unsigned u = u_first; u < u_last; u += u_step, ++i) {
-            const unsigned left = m.row_bytes - u * kUnitBytes;
-            const unsigned nblk = left >= (unsigned) kUnitBytes ? kUnitBlocks : (left + kBlk - 1) / kBlk;
+        unsigned s = 0, ph = 0, stops = 0;
+        for (unsigned i = 0; stops < (unsigned) G; ++i) {
             const unsigned b = i % kAccBufs, use = i / kAccBufs;
             mbar_wait(&tempty[b], (use & 1) ^ 1);
             mbar_wait(&full[s], ph);
             tc_fence_after();
+            const unsigned u = *reinterpret_cast<volatile unsigned *>(&unit_pub[i & 31]);
+            if (u == kNoUnit) {
+                // pass the stop mark on: the commit arrives once every earlier MMA has completed
+                ++stops;
+                if (elect_one())
+                    mma_commit(&tfull[b]);
+                __syncwarp();
+                if (++s == m.stages) {
+                    s = 0;
+                    ph ^= 1;
+                }
+                continue;
+            }
+            const unsigned left = m.row_bytes - u * kUnitBytes;
+            const unsigned nblk = left >= (unsigned) kUnitBytes ? kUnitBlocks : (left + kBlk - 1) / kBlk;
             if (elect_one()) {
                 // A: 32 lights = 4 swizzle atoms of 8 rows x 128 B (SBO = atom stride); B: two 16-byte K chunks
                 // 512 B apart (LBO), 8-column groups 128 B apart (SBO), 1024 B per 32 lights
@@ -352,15 +394,15 @@ fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         for (int k = 0; k < PTM_NCOEF; ++k)
             sc[k] = m.scale[k];
 
-        unsigned i = 0;
-        for (unsigned u = u_first; u < u_last; u += u_step, ++i) {
-            if (i % G != g)
-                continue;
+        for (unsigned i = g;; i += G) {
             const unsigned b = i % kAccBufs, use = i / kAccBufs;
-            const unsigned valid = (m.tail_px && u + 1 == m.n_units) ? m.tail_px : kUnitPx;
-            const size_t px0 = (size_t) u * kUnitPx;
             mbar_wait(&tfull[b], use & 1);
             tc_fence_after();
+            const unsigned u = *reinterpret_cast<volatile unsigned *>(&unit_pub[i & 31]);
+            if (u == kNoUnit)
+                break;
+            const unsigned valid = (m.tail_px && u + 1 == m.n_units) ? m.tail_px : kUnitPx;
+            const size_t px0 = (size_t) u * kUnitPx;
 
             if (kDebug != 0) {
                 int v[32];
@@ -737,16 +779,20 @@ cudaError_t launch_fit_mma(const FitArgs &a, int mode, int sm_count, cudaStream_
     unsigned grid = (unsigned) sm_count;
     if ((size_t) grid > n_units)
         grid = (unsigned) n_units;
-    static int sched = -1;
-    if (sched < 0) {
-        const char *v = getenv("PTM_MMA_SCHED");
-        sched = v ? atoi(v) : 1;
+    static int run_units = -1;
+    if (run_units < 0) {
+        const char *v = getenv("PTM_MMA_RUN");   // tuning aid: units per run
+        run_units = v ? atoi(v) : 8;
+        if (run_units < 1)
+            run_units = 1;
     }
-    m.chunk = 0;
-    if (sched == 1) {
-        m.chunk = (unsigned) ((n_units + grid - 1) / grid);
-        grid = (unsigned) ((n_units + m.chunk - 1) / m.chunk);
-    }
+    m.run_units = (unsigned) run_units;
+    m.counter = a.tile_counter;
+    const size_t n_runs = (n_units + m.run_units - 1) / m.run_units;
+    if ((size_t) grid > n_runs)
+        grid = (unsigned) n_runs;
+    // Invariant: the run counter is 0 between launches.  The hand-off block of a fused launch resets it on the
+    // device; any other launch is followed by a stream-ordered clear (below).
     cudaError_t e;
     switch (variant) {
     case 1:
@@ -766,6 +812,8 @@ cudaError_t launch_fit_mma(const FitArgs &a, int mode, int sm_count, cudaStream_
     if (e == cudaSuccess) {
         *done = full_units * unit_px + tail_px;
         ++g_mma_launches;
+        if (m.counter && !a.handoff.ticket)
+            e = cudaMemsetAsync(m.counter, 0, sizeof(unsigned), st);
     }
     return e;
 }

@@ -373,12 +373,8 @@ static cudaError_t launch_variant(const FitArgs &a, size_t n_tiles, unsigned tai
     size_t grid = (size_t) sm_count * per_sm_cache[dev][slot];
     if (grid > n_tiles)
         grid = n_tiles;
-    if (a.tile_counter && !a.handoff.ticket) {
-        // no hand-off block to reset the tile counter after the launch: clear it in stream order before
-        e = cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned), st);
-        if (e != cudaSuccess)
-            return e;
-    }
+    // Invariant: the tile counter is 0 between launches.  The hand-off block of a fused launch resets it on
+    // the device; any other launch is followed by a stream-ordered clear (below).
     if (a.handoff.ticket) {
         // fused encode: K1 -> K2 -> K1 -> ... each launched programmatically dependent on its predecessor
         cudaLaunchConfig_t cfg = {};
@@ -394,7 +390,10 @@ static cudaError_t launch_variant(const FitArgs &a, size_t n_tiles, unsigned tai
         return cudaLaunchKernelEx(&cfg, kern, a, (unsigned) n_tiles, tail_px);
     }
     kern<<<(unsigned) grid, kTmaThreads, Smem::total(a.n_lights), st>>>(a, (unsigned) n_tiles, tail_px);
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (e == cudaSuccess && a.tile_counter)
+        e = cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned), st);
+    return e;
 }
 
 // ---------------------------------------------------------------------------

@@ -116,6 +116,40 @@ def test_lrgb_encode_vs_oracle(ctx, oracle, dome1, M60, W, H, seed):
             assert_bytes_close(got["coef"], want["coef"], "LRGB coefficient bytes %dx%d" % (W, H), 0.02)
 
 
+@pytest.mark.parametrize("engine", ["ffma", "mma"])
+def test_plain_and_fused_entry_points_interleave(ctx, oracle, dome1, M60, engine):
+    """The dynamic tile schedule keeps a device counter at 0 between launches; the plain fit (cleared by a
+    stream-ordered memset) and the fused encode (cleared by the hand-off block) must be able to alternate
+    on one context, at a size where most tiles are drawn from the counter."""
+    from rti_b200.device import NCOEF, U8, light_q14
+    W, H = 2000, 752
+    P = W * H
+    n = len(dome1)
+    ctx.set_fit_engine(engine)
+    ctx.set_matrix(M60)
+    stack = torch.empty((n, P, 3), dtype=torch.uint8, device="cuda")
+    ctx.synth(0x5EED0009, 0, U8, 0, P, light_q14(dome1), stack, P * 3)
+    results = []
+    for fused in (False, True, False, True, True, False):
+        coeffs = torch.empty((P, NCOEF), dtype=torch.float32, device="cuda")
+        rgb = torch.zeros((P, 3), dtype=torch.uint8, device="cuda")
+        coef = torch.zeros((P, NCOEF), dtype=torch.uint8, device="cuda")
+        sb = torch.empty(12, dtype=torch.int32, device="cuda")
+        if fused:
+            ctx.encode_lrgb_dev(stack, P * 3, P, coeffs, rgb, coef, sb)
+        else:
+            keys = torch.empty(12, dtype=torch.int32, device="cuda")
+            ctx.keys_init(keys)
+            ctx.fit_lrgb(stack, P * 3, P, coeffs, rgb, keys)
+            ctx.quantise(coeffs, P, keys, coef, sb)
+        torch.cuda.synchronize()
+        results.append((rgb, coef, coeffs))
+    ctx.set_fit_engine("default")
+    for rgb, coef, coeffs in results[1:]:
+        assert torch.equal(rgb, results[0][0]) and torch.equal(coef, results[0][1])
+        assert torch.equal(coeffs, results[0][2])
+
+
 def test_degenerate_inputs_follow_the_reference(ctx, oracle, dome1, M60):
     """Inputs the reference does not guard against (rti-builder/ptm-encoder.c:342 divides by the mean luma,
     rti-builder/ptmlib.c:860-862 by the coefficient range): a pixel that is black in every image gets NaN
