@@ -329,8 +329,10 @@ fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             if (u == kNoUnit) {
                 // pass the stop mark on: the commit arrives once every earlier MMA has completed
                 ++stops;
-                if (elect_one())
+                if (elect_one()) {
+                    mma_commit(&empty[s]);   // the producer may need this stage for a later stop mark
                     mma_commit(&tfull[b]);
+                }
                 __syncwarp();
                 if (++s == m.stages) {
                     s = 0;
