@@ -702,7 +702,11 @@ cudaError_t launch_fit_mma(const FitArgs &a, int mode, int sm_count, cudaStream_
         const char *v = getenv("PTM_MMA_VARIANT");   // tuning aid; the default is what ships
         variant = v ? atoi(v) : 0;
     }
+#ifdef PTM_TUNING
     const int G = variant == 1 ? 4 : 2;
+#else
+    const int G = 2;
+#endif
     MmaArgs m;
     m.digits = a.digits;
     memcpy(m.scale, a.digit_scale, sizeof(m.scale));
@@ -797,11 +801,11 @@ cudaError_t launch_fit_mma(const FitArgs &a, int mode, int sm_count, cudaStream_
     // device; any other launch is followed by a stream-ordered clear (below).
     cudaError_t e;
     switch (variant) {
+#ifdef PTM_TUNING   // make EXTRA_NVFLAGS=-DPTM_TUNING: 1 = four epilogue groups; 2-4 = ceilings only, they skip work and do NOT produce results
     case 1:
         e = mode == 0 ? launch_mode<0, 4>(maps, a, m, smem, grid, st)
             : mode == 1 ? launch_mode<1, 4>(maps, a, m, smem, grid, st) : launch_mode<2, 4>(maps, a, m, smem, grid, st);
         break;
-#ifdef PTM_TUNING   // ceilings only: these variants skip work and do NOT produce results (make EXTRA_NVFLAGS=-DPTM_TUNING)
     case 2: e = mode == 2 ? launch_mode<2, 2, 1>(maps, a, m, smem, grid, st) : launch_mode<1, 2, 1>(maps, a, m, smem, grid, st); break;
     case 3: e = mode == 2 ? launch_mode<2, 2, 2>(maps, a, m, smem, grid, st) : launch_mode<1, 2, 2>(maps, a, m, smem, grid, st); break;
     case 4: e = mode == 2 ? launch_mode<2, 2, 3>(maps, a, m, smem, grid, st) : launch_mode<1, 2, 3>(maps, a, m, smem, grid, st); break;

@@ -59,6 +59,7 @@ fit_u16_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
     constexpr int kAcc = kRgb ? 12 : 4;   // fits per lane: 4 pixels x (3 channels | luma)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ int keys_s[2 * PTM_NCOEF];
+    __shared__ unsigned tile_pub[2];   // dynamic tile schedule, see fit_lrgb_u8_tma_kernel
     uint8_t *ring = smem;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + Smem::bars);
     uint64_t *empty = full + S;
@@ -87,15 +88,32 @@ fit_u16_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
     if (warp == k16Warps) {
         // ------------------------------------------------------------ producer
         const uint64_t policy = l2_policy_evict_first();
-        unsigned s = 0, ph = 0;
-        for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        unsigned s = 0, ph = 0, slot = 0;
+        unsigned tile = blockIdx.x;
+        for (;;) {
+            if (lane == 0) {
+                mbar_wait(&empty[s], ph ^ 1);
+                tile_pub[slot] = tile;
+            }
+            if (tile >= n_tiles) {
+                if (lane == 0)
+                    mbar_arrive(&full[s]);             // wake the consumers: nothing more to do
+                break;
+            }
+            unsigned next = tile + gridDim.x;
+            if (a.tile_counter) {                      // the next tile's draw hides behind this tile's copies
+                if (lane == 0)
+                    next = gridDim.x + atomicAdd(a.tile_counter, 1u);
+                next = __shfl_sync(0xFFFFFFFFu, next, 0);
+            }
             const uint8_t *src = a.stack + (size_t) tile * k16TileBytes + (size_t) lane * a.image_stride;
             const unsigned bytes = (tail_px && tile + 1 == n_tiles) ? tail_px * 6 : (unsigned) k16TileBytes;
             for (unsigned c = 0; c < n_chunks; ++c) {
                 const unsigned l0 = c * L;
                 const unsigned cnt = kFull ? (unsigned) L : min((unsigned) L, n - l0);
                 if (lane == 0) {
-                    mbar_wait(&empty[s], ph ^ 1);
+                    if (c != 0)
+                        mbar_wait(&empty[s], ph ^ 1);
                     mbar_arrive_expect_tx(&full[s], cnt * bytes);
                 }
                 __syncwarp();
@@ -107,12 +125,16 @@ fit_u16_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
                     ph ^= 1;
                 }
             }
+            tile = next;
+            slot ^= 1;
         }
     } else {
         // ----------------------------------------------------------- consumers
         const unsigned t = threadIdx.x;  // owns pixels 4t..4t+3 of the tile
-        unsigned s = 0, ph = 0;
-        for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        unsigned s = 0, ph = 0, slot = 0;
+        for (;; slot ^= 1) {
+            unsigned tile = 0;
+            bool stop = false;
             unsigned long long acc[kAcc][3];
 #pragma unroll
             for (int j = 0; j < kAcc; ++j)
@@ -121,6 +143,13 @@ fit_u16_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
 
             for (unsigned c = 0; c < n_chunks; ++c) {
                 mbar_wait(&full[s], ph);
+                if (c == 0) {
+                    tile = *reinterpret_cast<volatile unsigned *>(&tile_pub[slot]);
+                    if (tile >= n_tiles) {
+                        stop = true;
+                        break;
+                    }
+                }
                 const uint8_t *buf = ring + (size_t) s * Smem::stage_bytes + (size_t) t * 24;
                 const unsigned l0 = c * L;
                 const unsigned cnt = kFull ? (unsigned) L : min((unsigned) L, n - l0);
@@ -159,6 +188,8 @@ fit_u16_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
                     ph ^= 1;
                 }
             }
+            if (stop)
+                break;
 
             const unsigned tile_px = (tail_px && tile + 1 == n_tiles) ? tail_px : (unsigned) k16TilePx;
             const unsigned valid = min(128u, tile_px > warp * 128 ? tile_px - warp * 128 : 0u);
@@ -277,7 +308,10 @@ static cudaError_t launch16(const FitArgs &a, size_t n_tiles, unsigned tail_px, 
     if (grid > n_tiles)
         grid = n_tiles;
     kern<<<(unsigned) grid, k16Threads, Smem::total(a.n_lights), st>>>(a, (unsigned) n_tiles, tail_px);
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (e == cudaSuccess && a.tile_counter)   // the tile counter is 0 between launches
+        e = cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned), st);
+    return e;
 }
 
 // Streaming fit of a uint16 stack over whole 896-pixel tiles (+ a partial tile whose pixel count is a
