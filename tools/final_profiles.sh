@@ -12,7 +12,7 @@ python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $O/final_plain
 ncu --set full --clock-control none --import-source on -k regex:"fit_lrgb_u8_tma|quantise" -s 8 -c 2 -o $O/final_prof_k1k2 \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $O/final_ncu_k1k2.log 2>&1
 ENGINES=mma python tools/bench_engines.py 6000 4000 2 > $O/final_plain3.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:fit_mma -s 9 -c 1 -o $O/final_prof_mma_rgb \
+ncu --set full --clock-control none --import-source on -k regex:fit_mma -s 12 -c 1 -o $O/final_prof_mma_rgb \
     env ENGINES=mma python tools/bench_engines.py 6000 4000 2 > $O/final_ncu_mma.log 2>&1
 python tools/bench_engines.py > $O/final_engines.txt 2> $O/final_engines.err
 for e in ffma mma; do echo "engine $e"; PTM_FIT_ENGINE=$e python tools/bench_formats.py 50; done > $O/final_formats.txt 2> $O/final_formats.err
