@@ -217,7 +217,19 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         bind_to_gpu_numa_node(physical_gpu_index(local))
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL announces its version on stdout at communicator creation when NCCL_DEBUG=VERSION is set in the
+        # environment; stdout must carry the one JSON line only, so it points at stderr until NCCL is up
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
 
     W, H = args.width, args.height
