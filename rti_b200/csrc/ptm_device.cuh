@@ -136,23 +136,30 @@ __device__ __forceinline__ void keys_handoff(const Handoff &h, int *keys, int ma
         return;
     __threadfence();
     const int parity = h.epoch & 1;
-    if (threadIdx.x < 2 * PTM_NCOEF) {
-        const int v = atomicExch(&keys[threadIdx.x], float_to_key(-FLT_MAX));
-        for (int r = 0; r < h.world; ++r) {
-            int *slots = h.mailbox[r] + Layout::slots_off / sizeof(int);
-            slots[(parity * max_ranks + h.rank) * slot_ints + threadIdx.x] = v;
-        }
-    }
+    // the merged keys leave the accumulator (which is reset for the next launch) through shared memory;
+    // lane r then fills slot [parity][rank] of rank r's mailbox, fences ONCE and raises that rank's flag
+    __shared__ int merged_s[2 * PTM_NCOEF];
+    if (threadIdx.x < 2 * PTM_NCOEF)
+        merged_s[threadIdx.x] = atomicExch(&keys[threadIdx.x], float_to_key(-FLT_MAX));
     if (threadIdx.x == 0) {
         *h.ticket = 0;   // before the flags: once they are up the next fit may be on its way
         if (h.tile_counter)
             *h.tile_counter = 0;   // every block has stopped drawing tiles before it took its ticket
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x < h.world) {
-        volatile int *flags = h.mailbox[threadIdx.x] + Layout::flags_off / sizeof(int);
-        __threadfence_system();
+        int *box = h.mailbox[threadIdx.x];
+        int *slot = box + Layout::slots_off / sizeof(int) + (parity * max_ranks + h.rank) * slot_ints;
+#pragma unroll
+        for (int k = 0; k < 2 * PTM_NCOEF; ++k)
+            slot[k] = merged_s[k];
+        // one mailbox on this GPU: device scope is enough; peers over NVLink need system scope.  Thread 0's
+        // resets above are ordered before the flag by the block barrier and this fence (cumulativity).
+        if (h.world == 1)
+            __threadfence();
+        else
+            __threadfence_system();
+        volatile int *flags = box + Layout::flags_off / sizeof(int);
         flags[parity * max_ranks + h.rank] = (int) h.epoch;
     }
 }
