@@ -306,7 +306,8 @@ def run_b200(args):
         keys = torch.empty(12, dtype=torch.int32, device="cuda")
 
         def e2e_step():
-            ctx.encode_host_fit(host_stack.data_ptr(), (N_LIGHTS, rows, W), U8, M, planes=1, keys_out=keys)
+            ctx.encode_host_fit(host_stack.data_ptr(), (N_LIGHTS, rows, W), U8, M, planes=1, keys_out=keys,
+                                early_rgb=out_rgb)
             allreduce_keys(keys)
             return ctx.encode_host_finish(keys, [out_coef, out_rgb])
 
@@ -322,6 +323,7 @@ def run_b200(args):
         e2e_s = dt.item() / args.e2e_steps
         # the host path must give the same bytes as the device-resident one
         assert torch.equal(out_coef.reshape(-1, 6), enc.coef_bytes[0].cpu()), "e2e bytes differ from device path"
+        assert torch.equal(out_rgb.reshape(-1, 3), enc.rgb.cpu()), "e2e colour block differs from device path"
         assert torch.equal(out_rgb.reshape(-1, 3), enc.rgb.cpu())
         e2e = {"value": W * H / e2e_s / 1e6, "unit": "Mpixel/s",
                "h2d_bytes_per_step": int(host_stack.numel()), "d2h_bytes_per_step": int(out_coef.numel() + out_rgb.numel()),

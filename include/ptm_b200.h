@@ -179,6 +179,11 @@ int ptmb_synth (ptmb_ctx_t *ctx, uint32_t seed, int mode, int sample_type, uint3
  * the device (copied to keys_dev when non-NULL) so a multi-GPU caller can MAX-all-reduce
  * them before _finish (keys_dev NULL = the context's own keys).  _finish is synchronous.
  * Scratch is kept in the context between calls; _release frees it. */
+/* Optional, LRGB only: where the RGB block of the NEXT ptmb_encode_host_fit goes on the HOST.  The block is
+ * final after K1, so each slab's part is copied back on its own stream while later slabs are still coming
+ * up (PCIe carries both directions at once); ptmb_encode_host_finish then skips blocks_host[1] if it is the
+ * same pointer.  NULL (the default after every finish) = everything is copied in finish. */
+int ptmb_encode_host_early_rgb (ptmb_ctx_t *ctx, uint8_t *rgb_host);
 int ptmb_encode_host_fit (ptmb_ctx_t *ctx, const void *stack_host, int sample_type, size_t width, size_t height,
                           unsigned n_lights, const float *M, int format_planes, int32_t *keys_dev);
 int ptmb_encode_host_finish (ptmb_ctx_t *ctx, const int32_t *keys_dev, uint8_t *const *blocks_host,

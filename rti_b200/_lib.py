@@ -57,6 +57,7 @@ _SIGNATURES = {
     "ptmb_relight_rgb": ([_vp, _vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, C.c_uint, _vp], _int),
     "ptmb_selftest_div255": ([_vp, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)], _int),
     "ptmb_synth": ([_vp, _u32, _int, _int, _u32, _sz, C.c_uint, _vp, _vp, _sz], _int),
+    "ptmb_encode_host_early_rgb": ([_vp, _vp], _int),
     "ptmb_encode_host_fit": ([_vp, _vp, _int, _sz, _sz, C.c_uint, _vp, _int, _vp], _int),
     "ptmb_encode_host_finish": ([_vp, _vp, C.POINTER(_vp), _vp, _vp], _int),
     "ptmb_encode_host_release": ([_vp], _int),

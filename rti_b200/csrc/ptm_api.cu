@@ -578,8 +578,21 @@ static void encode_scratch_release(ptmb_ctx *c) {
     if (s.copy)
         cudaStreamDestroy(s.copy);
     s.copy = nullptr;
+    if (s.back)
+        cudaStreamDestroy(s.back);
+    s.back = nullptr;
+    if (s.fitted)
+        cudaEventDestroy(s.fitted);
+    s.fitted = nullptr;
+    s.early_rgb = s.early_rgb_done = nullptr;
     s.stage_bytes = s.coeff_floats = s.out_bytes = 0;
     s.valid = false;
+}
+
+int ptmb_encode_host_early_rgb(ptmb_ctx_t *c, uint8_t *rgb_host) {
+    REQUIRE(c, "ctx is NULL");
+    c->enc.early_rgb = rgb_host;
+    return 0;
 }
 
 int ptmb_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, int sample_type, size_t width, size_t height,
@@ -611,6 +624,13 @@ int ptmb_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, int sample_type,
 
     EncodeScratch &s = c->enc;
     s.valid = false;
+    if (!s.back) {
+        CK(cudaStreamCreateWithFlags(&s.back, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s.fitted, cudaEventDisableTiming));
+    }
+    uint8_t *const early = format_planes == 1 ? s.early_rgb : nullptr;
+    s.early_rgb = nullptr;
+    s.early_rgb_done = nullptr;
     if (!s.copy) {
         CK(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
@@ -674,6 +694,15 @@ int ptmb_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, int sample_type,
             CK(ptm::launch_fit_rgb(a, sample_type, c->sm_count, c->stream));
         }
         CK(cudaEventRecord(s.consumed[buf], c->stream));
+        if (early) {
+            // this slab's RGB bytes are final: send them home while the next slabs arrive
+            CK(cudaStreamWaitEvent(s.back, s.consumed[buf], 0));
+            CK(cudaMemcpyAsync(early + px0 * 3, rgb_dev + px0 * 3, npx * 3, cudaMemcpyDeviceToHost, s.back));
+        }
+    }
+    if (early) {
+        CK(cudaEventRecord(s.fitted, s.back));
+        s.early_rgb_done = early;
     }
     if (keys_dev)
         CK(cudaMemcpyAsync(keys_dev, c->keys_dev, PTMB_KEYS * sizeof(int32_t), cudaMemcpyDeviceToDevice,
@@ -698,20 +727,27 @@ int ptmb_encode_host_finish(ptmb_ctx_t *c, const int32_t *keys_dev, uint8_t *con
     for (int b = 0; b < s.planes; ++b)
         CK(cudaMemcpyAsync(blocks_host[b], s.bytes + (size_t) b * pixels * PTMB_COEFFICIENTS,
                            pixels * PTMB_COEFFICIENTS, cudaMemcpyDeviceToHost, c->stream));
-    if (s.planes == 1)
-        CK(cudaMemcpyAsync(blocks_host[1], rgb_dev, pixels * 3, cudaMemcpyDeviceToHost, c->stream));
+    if (s.planes == 1) {
+        if (s.early_rgb_done && s.early_rgb_done == blocks_host[1])
+            CK(cudaStreamWaitEvent(c->stream, s.fitted, 0));   // already on its way / there
+        else
+            CK(cudaMemcpyAsync(blocks_host[1], rgb_dev, pixels * 3, cudaMemcpyDeviceToHost, c->stream));
+    }
     if (coeffs_host)
         CK(cudaMemcpyAsync(coeffs_host, s.coeffs, plane_floats * s.planes * sizeof(float), cudaMemcpyDeviceToHost,
                            c->stream));
     CK(cudaMemcpyAsync(sb_host, c->sb_dev, sizeof(ptmb_scale_bias_t), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     s.valid = false;
+    s.early_rgb_done = nullptr;
     return 0;
 }
 
 int ptmb_encode_host(ptmb_ctx_t *c, const void *stack_host, int sample_type, size_t width, size_t height,
                      unsigned n_lights, const float *M, int format_planes, uint8_t *const *blocks_host,
                      float *coeffs_host, ptmb_scale_bias_t *sb_host) {
+    if (format_planes == 1 && blocks_host && ptmb_encode_host_early_rgb(c, blocks_host[1]))
+        return 1;
     if (ptmb_encode_host_fit(c, stack_host, sample_type, width, height, n_lights, M, format_planes, nullptr))
         return 1;
     return ptmb_encode_host_finish(c, nullptr, blocks_host, coeffs_host, sb_host);

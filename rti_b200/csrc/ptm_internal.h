@@ -14,6 +14,10 @@ struct EncodeScratch {
     uint8_t *bytes = nullptr;  // planes * pixels * 6 (+ pixels * 3 for LRGB)
     size_t out_bytes = 0;
     cudaStream_t copy = nullptr;
+    cudaStream_t back = nullptr;          // device -> host copies that overlap the fit (early RGB block)
+    cudaEvent_t fitted = nullptr;
+    uint8_t *early_rgb = nullptr;         // host destination set by ptmb_encode_host_early_rgb, consumed by the next fit
+    uint8_t *early_rgb_done = nullptr;    // what the last fit already copied back
     cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
     size_t pixels = 0;
     int planes = 0;

@@ -194,11 +194,15 @@ class Context:
         _lib.check(self._lib.ptmb_synth(self._h, seed, mode, sample_type, pixel0, pixels, lq.shape[0],
                                         lq.ctypes.data, _ptr(stack), image_stride))
 
-    def encode_host_fit(self, stack, shape, sample_type, M, planes=1, keys_out=None):
+    def encode_host_fit(self, stack, shape, sample_type, M, planes=1, keys_out=None, early_rgb=None):
         """First half of the host-buffer encode: stream the HOST stack (address or numpy array,
         [n][H][W][3]) through K1.  Leaves the extrema keys on the device (copied to
-        ``keys_out`` if given) so that ranks can exchange them before encode_host_finish."""
+        ``keys_out`` if given) so that ranks can exchange them before encode_host_finish.
+        ``early_rgb`` (LRGB): host destination of the RGB block, filled slab by slab during the fit;
+        pass the same buffer as out[1] of encode_host_finish."""
         n, H, W = shape
+        if early_rgb is not None:
+            _lib.check(self._lib.ptmb_encode_host_early_rgb(self._h, _ptr(early_rgb)))
         M = np.ascontiguousarray(M, dtype=np.float32)
         self._enc_geom = (H, W, planes)
         _lib.check(self._lib.ptmb_encode_host_fit(self._h, _ptr(stack), sample_type, W, H, n, M.ctypes.data,
