@@ -150,6 +150,29 @@ def test_plain_and_fused_entry_points_interleave(ctx, oracle, dome1, M60, engine
         assert torch.equal(coeffs, results[0][2])
 
 
+@pytest.mark.parametrize("engine", ["ffma", "mma"])
+def test_fused_encode_loop_is_deterministic(oracle, dome1, M60, engine):
+    """Back-to-back fused encodes (every launch programmatically dependent on its predecessor, tiles drawn from
+    the device counter, keys handed over through the mailbox): whichever block takes which tile, every result
+    equals the first bit for bit.  tools/soak.py runs the same for thousands of encodes at the bench sizes."""
+    from rti_b200.device import U8, light_q14
+    from rti_b200.encoder import PtmEncoder
+    for W, H, reps in ((2000, 37, 300), (2000, 752, 60)):
+        P = W * H
+        stack = torch.empty((len(dome1), H, W, 3), dtype=torch.uint8, device="cuda")
+        enc = PtmEncoder(W, H, M60, engine=engine)
+        enc.ctx.synth(0x5EED0001, 0, U8, 0, P, light_q14(dome1), stack, P * 3)
+        enc.encode(stack)
+        torch.cuda.synchronize()
+        ref = (enc.coef_bytes.clone(), enc.rgb.clone(), enc.coeffs.clone(), enc.sb.clone())
+        for i in range(reps):
+            enc.encode(stack)
+            if i % 29 == 0 or i == reps - 1:
+                torch.cuda.synchronize()
+                assert torch.equal(enc.coef_bytes, ref[0]) and torch.equal(enc.rgb, ref[1])
+                assert torch.equal(enc.coeffs, ref[2]) and torch.equal(enc.sb, ref[3])
+
+
 def test_degenerate_inputs_follow_the_reference(ctx, oracle, dome1, M60):
     """Inputs the reference does not guard against (rti-builder/ptm-encoder.c:342 divides by the mean luma,
     rti-builder/ptmlib.c:860-862 by the coefficient range): a pixel that is black in every image gets NaN
