@@ -388,7 +388,11 @@ cudaError_t launch_fit_lrgb(const FitArgs &a, int sample_type, int sm_count, cud
     const size_t gen_smem = (size_t) a.n_lights * PTM_NCOEF * sizeof(float);
     if (sample_type == 1) {   // 16-bit stacks: streaming kernel over the tiles, generic kernel for the rest
         size_t done16 = 0;
-        cudaError_t e16 = launch_fit_u16_tma(a, false, sm_count, st, &done16);
+        cudaError_t e16 = cudaSuccess;
+        if (resolve_engine(a.engine, kDefaultEngineLrgbU16) == 2)
+            e16 = launch_fit_mma(a, 3, sm_count, st, &done16);
+        if (e16 == cudaSuccess && done16 == 0)
+            e16 = launch_fit_u16_tma(a, false, sm_count, st, &done16);
         if (e16 != cudaSuccess)
             return e16;
         if (done16 < a.pixels) {

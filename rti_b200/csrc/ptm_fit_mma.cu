@@ -564,6 +564,94 @@ fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                                  valid * 24);
                     bulk_commit();
                 }
+            } else if (kMode == 3) {
+                // LRGB on 16-bit samples (no counterpart in the reference; semantics of oracle/ptm_oracle.c:
+                // orc_lrgb16_finish and of fit_u16_tma_kernel).  Lanes come in (low byte, high byte) pairs; pair
+                // j = r / 2 holds sample 64 c + j of column block c, whose channel is (c + j) % 3: each pair
+                // owns exactly one luma sample, i.e. finishes one of the unit's 64 pixels.
+                const bool odd = (r & 1) != 0;
+                const unsigned j = r >> 1;
+                const unsigned cy = (3u - j % 3u) % 3u;       // the block in which this pair's sample is luma
+                int sums[kUnitBlocks];
+                long long t[PTM_NCOEF] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+                for (int c = 0; c < kUnitBlocks; ++c) {
+                    int v[32];
+                    tmem_ld32(lane_base + b * kAccCols + c * kNB, v);
+                    sums[c] = v[kSumCol];
+                    if (cy == (unsigned) c) {
+#pragma unroll
+                        for (int k = 0; k < PTM_NCOEF; ++k)
+                            t[k] = digits_to_int(&v[4 * k]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(&tempty[b]);
+                // 16-bit sums and truncated means of the pair's three samples
+                uint16_t *means = reinterpret_cast<uint16_t *>(stg + kStagePlane + 384);
+                unsigned mean[kUnitBlocks];
+#pragma unroll
+                for (int c = 0; c < kUnitBlocks; ++c) {
+                    const int other = __shfl_xor_sync(0xFFFFFFFFu, sums[c], 1);
+                    const unsigned s16 = odd ? (unsigned) other + 256u * (unsigned) sums[c]
+                                             : (unsigned) sums[c] + 256u * (unsigned) other;
+                    mean[c] = s16 / a.n_lights;
+                    if (!odd)
+                        means[c * 64 + j] = (uint16_t) mean[c];
+                }
+                const unsigned ya = cy == 0 ? mean[0] : cy == 1 ? mean[1] : mean[2];
+                // the even lane finishes coefficients 0..2 of the luma fit, the odd lane 3..5
+                float f[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const long long send = odd ? t[k] : t[3 + k];
+                    const long long recv = __shfl_xor_sync(0xFFFFFFFFu, send, 1);
+                    const long long whole = odd ? recv + 256 * t[3 + k] : t[k] + 256 * recv;
+                    f[k] = __fmul_rn(__ll2float_rn(whole), odd ? sc[3 + k] : sc[k]);
+                }
+                if (issuer)
+                    bulk_wait_read();
+                group_sync(1 + g);
+                const unsigned q = (cy * 64 + j) / 3;         // this pair's pixel inside the unit
+                const unsigned cba = means[3 * q + 1], cra = means[3 * q + 2];
+                float dummy[PTM_NCOEF] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                unsigned R, Gc, B;
+                lrgb_finish(ya >> 8, cba >> 8, cra >> 8, dummy, R, Gc, B);
+                const float norm = __fdiv_rn(256.0f, (float) ya);
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    f[k] = __fmul_rn(f[k], norm);
+                if (q < valid) {
+#pragma unroll
+                    for (int k = 0; k < PTM_NCOEF; ++k) {
+                        if ((k >= 3) == odd) {
+                            ext.mn[k] = fminf(ext.mn[k], f[k % 3]);
+                            ext.mx[k] = fmaxf(ext.mx[k], f[k % 3]);
+                        }
+                    }
+                }
+                if (a.coeffs) {
+                    float *row = reinterpret_cast<float *>(stg + q * 24 + (odd ? 12 : 0));
+                    row[0] = f[0];
+                    row[1] = f[1];
+                    row[2] = f[2];
+                }
+                if (!odd) {
+                    uint8_t *rgb = stg + kStagePlane + 3 * q;
+                    rgb[0] = (uint8_t) R;
+                    rgb[1] = (uint8_t) Gc;
+                    rgb[2] = (uint8_t) B;
+                }
+                fence_async_smem();
+                group_sync(1 + g);
+                if (issuer) {
+                    if (a.coeffs)
+                        bulk_s2g(a.coeffs + px0 * PTM_NCOEF, stg, valid * 24);
+                    bulk_s2g(a.rgb + px0 * 3, stg + kStagePlane, valid * 3);
+                    bulk_commit();
+                }
             }
         }
         if (issuer) {
@@ -671,15 +759,15 @@ static cudaError_t launch_mode(const CUtensorMap *maps, const FitArgs &a, const 
     return cudaGetLastError();
 }
 
-// mode: 0 = RGB u8, 1 = LRGB u8, 2 = RGB u16.  Covers whole 384-byte units (+ a 16-pixel-granular partial
+// mode: 0 = RGB u8, 1 = LRGB u8, 2 = RGB u16, 3 = LRGB u16.  Covers whole 384-byte units (+ a 16-pixel-granular partial
 // last unit) and reports the pixels it covered through *done; 0 = layout not eligible.
 cudaError_t launch_fit_mma(const FitArgs &a, int mode, int sm_count, cudaStream_t st, size_t *done) {
     *done = 0;
-    if (mode < 0 || mode > 2)
+    if (mode < 0 || mode > 3)
         return cudaSuccess;
     if (!a.digits || a.kpad == 0 || a.kpad > 224 || a.n_lights > a.kpad)
         return cudaSuccess;
-    const unsigned unit_px = mode == 2 ? 64 : 128, px_bytes = mode == 2 ? 6 : 3;
+    const unsigned unit_px = mode >= 2 ? 64 : 128, px_bytes = mode >= 2 ? 6 : 3;
     const size_t row_bytes_all = a.pixels * px_bytes;
     bool ok = ((uintptr_t) a.stack % 16 == 0) && (a.image_stride % 16 == 0) && row_bytes_all < 0x7FFFFFFFull &&
               a.image_stride >= row_bytes_all;
@@ -800,7 +888,8 @@ cudaError_t launch_fit_mma(const FitArgs &a, int mode, int sm_count, cudaStream_
     // Invariant: the run counter is 0 between launches.  The hand-off block of a fused launch resets it on the
     // device; any other launch is followed by a stream-ordered clear (below).
     cudaError_t e;
-    switch (variant) {
+    switch (mode == 3 ? 0 : variant) {   // the tuning variants exist for modes 0-2
+
 #ifdef PTM_TUNING   // make EXTRA_NVFLAGS=-DPTM_TUNING: 1 = four epilogue groups; 2-4 = ceilings only, they skip work and do NOT produce results
     case 1:
         e = mode == 0 ? launch_mode<0, 4>(maps, a, m, smem, grid, st)
@@ -811,8 +900,10 @@ cudaError_t launch_fit_mma(const FitArgs &a, int mode, int sm_count, cudaStream_
     case 4: e = mode == 2 ? launch_mode<2, 2, 3>(maps, a, m, smem, grid, st) : launch_mode<1, 2, 3>(maps, a, m, smem, grid, st); break;
 #endif
     default:
-        e = mode == 0 ? launch_mode<0, 2>(maps, a, m, smem, grid, st)
-            : mode == 1 ? launch_mode<1, 2>(maps, a, m, smem, grid, st) : launch_mode<2, 2>(maps, a, m, smem, grid, st);
+        e = mode == 0   ? launch_mode<0, 2>(maps, a, m, smem, grid, st)
+            : mode == 1 ? launch_mode<1, 2>(maps, a, m, smem, grid, st)
+            : mode == 2 ? launch_mode<2, 2>(maps, a, m, smem, grid, st)
+                        : launch_mode<3, 2>(maps, a, m, smem, grid, st);
         break;
     }
     if (e == cudaSuccess) {

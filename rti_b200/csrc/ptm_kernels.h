@@ -74,6 +74,7 @@ bool pack_mma_digits(const float *M, unsigned n_lights, std::vector<int8_t> &ima
 constexpr int kDefaultEngineLrgbU8 = 1;
 constexpr int kDefaultEngineRgbU8 = 2;
 constexpr int kDefaultEngineRgbU16 = 2;
+constexpr int kDefaultEngineLrgbU16 = 1;
 int resolve_engine(int requested, int format_default);
 cudaError_t launch_keys_init(int *keys, cudaStream_t st);
 cudaError_t launch_fit_lrgb(const FitArgs &a, int sample_type, int sm_count, cudaStream_t st);

@@ -186,3 +186,36 @@ def test_rgb_u16_mma_vs_oracle(ctx, oracle, W, H, n):
     mm = np.concatenate([-f[:6], f[6:]])
     p0 = want["coeffs"][0].reshape(-1, 6)
     np.testing.assert_allclose(mm, np.concatenate([p0.min(0), p0.max(0)]), rtol=3e-5, atol=1e-2)
+
+
+@pytest.mark.parametrize("W,H,n", [(64, 1, 60), (80, 33, 60), (72, 33, 100), (512, 150, 100), (48, 5, 224)])
+def test_lrgb_u16_mma_vs_oracle(ctx, oracle, W, H, n):
+    """LRGB on 16-bit stacks (the extension stated in oracle/ptm_oracle.c:orc_lrgb16_finish): one pixel per
+    (low byte, high byte) lane pair, 16-bit means exchanged through shared memory."""
+    from rti_b200.device import U16
+    L = _ring_lights(n)
+    M = oracle.pinv(L)
+    P = W * H
+    y16 = oracle.synth_stack(0x7000 + n + W, 0, W, H, L, dtype=np.uint16)
+    want = oracle.encode_lrgb_u16(y16, M)
+    ctx.set_matrix(M)
+    c1 = torch.empty((P, 6), dtype=torch.float32, device="cuda")
+    rgb = torch.empty((P, 3), dtype=torch.uint8, device="cuda")
+    keys = torch.empty(12, dtype=torch.int32, device="cuda")
+    ctx.keys_init(keys)
+    before = ctx.mma_launches()
+    ctx.fit_lrgb(dev(y16.view(np.int16)).view(torch.uint16), P * 6, P, c1, rgb, keys, U16)
+    torch.cuda.synchronize()
+    assert ctx.mma_launches() == before + (1 if (P * 6) % 16 == 0 and P >= 16 else 0)
+    np.testing.assert_array_equal(rgb.cpu().numpy().reshape(H, W, 3), want["rgb"])
+    got = c1.cpu().numpy().reshape(H, W, 6)
+    norm = 256.0 / np.floor(y16[..., 0].astype(np.float64).sum(0) / n)
+    bound = np.einsum("kn,nhw->hwk", np.abs(M).astype(np.float64), y16[..., 0].astype(np.float64)) * norm[..., None]
+    err = (np.abs(got - want["coeffs"]) / bound).max()
+    print("normalised coefficient error %.3g" % err)
+    assert err <= 1e-5
+    from rti_b200.device import key_to_float
+    f = key_to_float(keys.cpu().numpy())
+    flat = want["coeffs"].reshape(-1, 6)
+    np.testing.assert_allclose(np.concatenate([-f[:6], f[6:]]), np.concatenate([flat.min(0), flat.max(0)]),
+                               rtol=3e-5, atol=1e-2)
