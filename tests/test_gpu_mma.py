@@ -90,7 +90,7 @@ def test_lrgb_mma_vs_oracle(ctx, oracle, dome1, M60, W, H):
         assert_bytes_close(got["coef"], want["coef"], "LRGB coefficient bytes (mma) %dx%d" % (W, H), 0.02)
 
 
-@pytest.mark.parametrize("n", [12, 32, 33, 100, 128, 160, 192, 224])
+@pytest.mark.parametrize("n", [6, 8, 12, 32, 33, 100, 128, 160, 192, 224])
 def test_mma_light_counts(ctx, oracle, n):
     """K padding (lights rounded up to 32), one to seven MMA steps per column block; light groups
     of 8 with and without a remainder group."""
