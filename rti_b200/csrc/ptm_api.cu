@@ -1,6 +1,7 @@
 // C ABI of libptm_b200.so (see include/ptm_b200.h).  Thin: argument checks,
 // context bookkeeping and launches; no arithmetic lives here.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -254,6 +255,12 @@ static int make_fit_args(ptmb_ctx_t *c, const void *stack_dev, size_t image_stri
     a.kpad = c->kpad;
     a.engine = c->engine;
     a.tile_counter = c->ticket_dev ? c->ticket_dev + 1 : nullptr;
+    static int store_hint = -1;
+    if (store_hint < 0) {
+        const char *v = getenv("PTM_K1_STORE_HINT");
+        store_hint = v ? atoi(v) : 2;
+    }
+    a.store_hint = store_hint;
     return 0;
 }
 

@@ -77,6 +77,7 @@ struct MmaArgs {
     unsigned tail_px;         // pixels of the last unit when it is partial, else 0
     unsigned row_bytes;       // bytes of one image that the units cover
     unsigned grouped;         // 1: whole units are loaded light-group-major (see the producer)
+    unsigned store_hint;      // L2 policy of the output bulk stores: 0 = none, 1 = evict_first, 2 = evict_last
     unsigned run_units;       // units per run: a CTA draws runs of consecutive units (DRAM row locality inside a run)
     unsigned *counter;        // device-wide run counter, 0 at launch (nullptr: runs strided by the grid)
 };
@@ -164,6 +165,18 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
                  "r"(smem_addr(src_smem)), "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void *dst_gmem, const void *src_smem, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+                 "r"(smem_addr(src_smem)), "r"(bytes), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void store_out(unsigned hint, uint64_t policy, void *dst_gmem, const void *src_smem,
+                                          uint32_t bytes) {
+    if (hint)
+        bulk_s2g_hint(dst_gmem, src_smem, bytes, policy);
+    else
+        bulk_s2g(dst_gmem, src_smem, bytes);
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -395,6 +408,11 @@ fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < PTM_NCOEF; ++k)
             sc[k] = m.scale[k];
+        uint64_t st_policy = 0;
+        if (m.store_hint == 1)
+            st_policy = l2_policy_evict_first();
+        else if (m.store_hint == 2)
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(st_policy));
 
         for (unsigned i = g;; i += G) {
             const unsigned b = i % kAccBufs, use = i / kAccBufs;
@@ -448,7 +466,7 @@ fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                 if (issuer) {
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch)
-                        bulk_s2g(a.coeffs + (size_t) ch * a.plane_stride + px0 * PTM_NCOEF, stg + ch * kStagePlane,
+                        store_out(m.store_hint, st_policy, a.coeffs + (size_t) ch * a.plane_stride + px0 * PTM_NCOEF, stg + ch * kStagePlane,
                                  valid * 24);
                     bulk_commit();
                 }
@@ -504,8 +522,8 @@ fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                 group_sync(1 + g);
                 if (issuer) {
                     if (a.coeffs)
-                        bulk_s2g(a.coeffs + px0 * PTM_NCOEF, stg, valid * 24);
-                    bulk_s2g(a.rgb + px0 * 3, stg + kStagePlane, valid * 3);
+                        store_out(m.store_hint, st_policy, a.coeffs + px0 * PTM_NCOEF, stg, valid * 24);
+                    store_out(m.store_hint, st_policy, a.rgb + px0 * 3, stg + kStagePlane, valid * 3);
                     bulk_commit();
                 }
             } else if (kMode == 2) {
@@ -560,7 +578,7 @@ fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                 if (issuer) {
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch)
-                        bulk_s2g(a.coeffs + (size_t) ch * a.plane_stride + px0 * PTM_NCOEF, stg + ch * kStagePlane,
+                        store_out(m.store_hint, st_policy, a.coeffs + (size_t) ch * a.plane_stride + px0 * PTM_NCOEF, stg + ch * kStagePlane,
                                  valid * 24);
                     bulk_commit();
                 }
@@ -648,8 +666,8 @@ fit_mma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                 group_sync(1 + g);
                 if (issuer) {
                     if (a.coeffs)
-                        bulk_s2g(a.coeffs + px0 * PTM_NCOEF, stg, valid * 24);
-                    bulk_s2g(a.rgb + px0 * 3, stg + kStagePlane, valid * 3);
+                        store_out(m.store_hint, st_policy, a.coeffs + px0 * PTM_NCOEF, stg, valid * 24);
+                    store_out(m.store_hint, st_policy, a.rgb + px0 * 3, stg + kStagePlane, valid * 3);
                     bulk_commit();
                 }
             }
@@ -880,6 +898,12 @@ cudaError_t launch_fit_mma(const FitArgs &a, int mode, int sm_count, cudaStream_
         if (run_units < 1)
             run_units = 1;
     }
+    static int store_hint = -1;
+    if (store_hint < 0) {
+        const char *v = getenv("PTM_MMA_STORE_HINT");
+        store_hint = v ? atoi(v) : 2;
+    }
+    m.store_hint = (unsigned) store_hint;
     m.run_units = (unsigned) run_units;
     m.counter = a.tile_counter;
     const size_t n_runs = (n_units + m.run_units - 1) / m.run_units;

@@ -104,6 +104,12 @@ __device__ __forceinline__ unsigned tile_px_of(unsigned tile, unsigned n_tiles, 
     return (tail_px && tile + 1 == n_tiles) ? tail_px : (unsigned) kTilePx;
 }
 
+__device__ __forceinline__ void st_hint(float4 *p, float4 v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w), "l"(policy)
+                 : "memory");
+}
+
 #ifdef PTM_TUNING
 // per-CTA timeline of the last launch: entry, first stage consumed, last tile stored, exit (globaltimer ns)
 __device__ unsigned long long g_cta_times[4 * 1024];
@@ -218,6 +224,11 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
         // ----------------------------------------------------------- consumers
         const unsigned t = threadIdx.x;  // 0..255, owns pixels 4t..4t+3 of the tile
         unsigned s = 0, ph = 0, slot = 0;
+        uint64_t st_policy = 0;
+        if (a.store_hint == 1)
+            st_policy = l2_policy_evict_first();
+        else if (a.store_hint == 2)
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(st_policy));
         for (bool first = true;; first = false, slot ^= 1) {
             unsigned tile = 0;
             float acc[4][PTM_NCOEF];
@@ -317,8 +328,12 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
                 const float4 *src = reinterpret_cast<const float4 *>(stg);
 #pragma unroll
                 for (int r = 0; r < 6; ++r)
-                    if (lane + 32 * r < valid * 6 / 4)
-                        __stcg(dst + lane + 32 * r, src[lane + 32 * r]);
+                    if (lane + 32 * r < valid * 6 / 4) {
+                        if (a.store_hint)
+                            st_hint(dst + lane + 32 * r, src[lane + 32 * r], st_policy);
+                        else
+                            __stcg(dst + lane + 32 * r, src[lane + 32 * r]);
+                    }
             }
             if (lane < valid * 3 / 16)
                 __stcg(reinterpret_cast<uint4 *>(a.rgb + wpx * 3) + lane,

@@ -56,6 +56,9 @@ struct FitArgs {
     float digit_scale[6];   // 2^-F_k
     unsigned kpad;          // lights rounded up to 32
     unsigned *tile_counter; // dynamic tile scheduling of the LRGB ring kernel: device counter, 0 at launch (nullptr = static)
+    // L2 policy of K1's coefficient stores: 0 = plain .cg stores, 1 = evict_first, 2 = evict_last (default: the
+    // float plane is what K2 reads next; kept with priority, part of it is still in L2 then)
+    int store_hint;
     int engine;             // PTMB_ENGINE_*: 0 = default choice, 1 = FFMA kernels, 2 = tensor-core kernel
 };
 
