@@ -49,6 +49,16 @@ __device__ __forceinline__ void fma3(unsigned long long (&c)[3], float v, unsign
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c[2]) : "l"(vv), "l"(m45));
 }
 
+// coefficient store with an L2 policy (FitArgs::store_hint), see fit_lrgb_u8_tma_kernel
+__device__ __forceinline__ void st_coeff16(float4 *p, float4 v, int hint, uint64_t policy) {
+    if (hint)
+        asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y),
+                     "f"(v.z), "f"(v.w), "l"(policy)
+                     : "memory");
+    else
+        __stcg(p, v);
+}
+
 __device__ __forceinline__ float pair_lo(unsigned long long p) { return __uint_as_float((unsigned) (p & 0xFFFFFFFFull)); }
 __device__ __forceinline__ float pair_hi(unsigned long long p) { return __uint_as_float((unsigned) (p >> 32)); }
 
@@ -132,6 +142,11 @@ fit_u16_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
         // ----------------------------------------------------------- consumers
         const unsigned t = threadIdx.x;  // owns pixels 4t..4t+3 of the tile
         unsigned s = 0, ph = 0, slot = 0;
+        uint64_t st_policy = 0;
+        if (a.store_hint == 1)
+            st_policy = l2_policy_evict_first();
+        else if (a.store_hint == 2)
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(st_policy));
         for (;; slot ^= 1) {
             unsigned tile = 0;
             bool stop = false;
@@ -239,7 +254,7 @@ fit_u16_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
 #pragma unroll
                     for (int r = 0; r < 6; ++r)
                         if (lane + 32 * r < valid * 6 / 4)
-                            __stcg(dst + lane + 32 * r, src[lane + 32 * r]);
+                            st_coeff16(dst + lane + 32 * r, src[lane + 32 * r], a.store_hint, st_policy);
                 }
                 if (lane < valid * 3 / 16)
                     __stcg(reinterpret_cast<uint4 *>(a.rgb + wpx * 3) + lane, reinterpret_cast<const uint4 *>(rgbw)[lane]);
@@ -271,7 +286,7 @@ fit_u16_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
 #pragma unroll
                     for (int r = 0; r < 6; ++r)
                         if (lane + 32 * r < valid * 6 / 4)
-                            __stcg(dst + lane + 32 * r, src[lane + 32 * r]);
+                            st_coeff16(dst + lane + 32 * r, src[lane + 32 * r], a.store_hint, st_policy);
                     __syncwarp();
                 }
             }
