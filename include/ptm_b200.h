@@ -150,6 +150,17 @@ int ptmb_quantise_consume (ptmb_ctx_t *ctx, float *coeffs_dev, size_t pixels, co
  * light directions at once.  uv: HOST array of n_dirs (u, v) pairs.  out_dev: uint8
  * [n_dirs][height][width][3], top row first (stored row height-1-y, :587-589).
  * LRGB: coef_dev [pixels][6] + rgb_dev [pixels][3].  RGB: three coefficient planes. */
+/* Arithmetic of K3:
+ *   PTMB_RELIGHT_EXACT  every intermediate rounding of the reference's loop is reproduced: rasters are
+ *                       bit-identical to the reference decoder's (issue bound, ~60 % of the HBM roofline)
+ *   PTMB_RELIGHT_FAST   fused multiply-adds, "/ 255" folded into the coefficients, integer CLIP: every byte is
+ *                       within +-1 of the reference's (the tolerance BASELINE.json states for relit output)
+ *   PTMB_RELIGHT_AUTO   (default) exact below 4 directions per call, fast for sweeps; the environment
+ *                       variable PTM_RELIGHT=exact|fast overrides AUTO. */
+#define PTMB_RELIGHT_AUTO  0
+#define PTMB_RELIGHT_EXACT 1
+#define PTMB_RELIGHT_FAST  2
+int ptmb_set_relight_mode (ptmb_ctx_t *ctx, int mode);
 int ptmb_relight_lrgb (ptmb_ctx_t *ctx, const uint8_t *coef_dev, const uint8_t *rgb_dev,
                        size_t width, size_t height, const float *scale, const int32_t *bias,
                        const float *uv, unsigned n_dirs, uint8_t *out_dev);

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "ptmb_minmax": ([_vp, _vp, _sz, _vp], _int),
     "ptmb_quantise": ([_vp, _vp, _sz, _vp, _vp, _vp], _int),
     "ptmb_quantise_consume": ([_vp, _vp, _sz, _vp, _vp, _vp], _int),
+    "ptmb_set_relight_mode": ([_vp, _int], _int),
     "ptmb_relight_lrgb": ([_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, C.c_uint, _vp], _int),
     "ptmb_relight_rgb": ([_vp, _vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, C.c_uint, _vp], _int),
     "ptmb_selftest_div255": ([_vp, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)], _int),

@@ -6,10 +6,12 @@
  * Relights the PTM for light (u, v) (default 0 0, ref :46-47) on the GPU and writes the image to
  * stdout through ptm_write_jpeg.
  */
+#define _POSIX_C_SOURCE 200809L
 #include <stdio.h>
 #include <stdlib.h>
 
 #include "../../../include/ptmlib.h"
+#include "cli_common.h"
 
 int main (int argc, char *argv[]) {
     if (argc != 2 && argc != 4) {
@@ -22,6 +24,7 @@ int main (int argc, char *argv[]) {
         sscanf (argv[2], "%f", &u);
         sscanf (argv[3], "%f", &v);
     }
+    cli_select_devices ();
     FILE *fp = fopen (argv[1], "rb");
     if (fp == NULL) {
         fprintf (stderr, "can't open %s\n", argv[1]);

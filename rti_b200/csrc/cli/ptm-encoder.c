@@ -24,6 +24,7 @@
 
 #include "../../../include/ptmlib.h"
 #include "../ptm_codec.h"
+#include "cli_common.h"
 
 const char *argp_program_version = "PTM Encoder 0.1 (B200)";
 
@@ -42,37 +43,35 @@ struct arguments {
     int verbose;
 };
 
+/* option handling; messages and exit codes as the reference prints them (ref :64-104) */
+static void list_formats_and_exit (void) {
+    printf ("Supported formats:\n");
+    for (const ptm_format_t *f = ptm_formats; f->name; ++f)
+        printf ("%s\n", f->name);
+    exit (0);
+}
+
 static error_t parse_opt (int key, char *arg, struct argp_state *state) {
     struct arguments *a = state->input;
-    switch (key) {
-    case 'f':
-        a->format = ptm_get_format (arg);
-        if (a->format == NULL) {
+    if (key == 'l')
+        list_formats_and_exit ();
+    if (key == 'v') {
+        a->verbose = 1;
+    } else if (key == 'o') {
+        a->filename_ptm = arg;
+    } else if (key == 'f') {
+        if (!(a->format = ptm_get_format (arg))) {
             fprintf (stderr, "No format by that name: %s\n", arg);
             exit (0);          /* the reference exits 0 here too (ref :69-72) */
         }
-        break;
-    case 'l':
-        printf ("Supported formats:\n");
-        for (const ptm_format_t *f = ptm_formats; f->name; ++f)
-            printf ("%s\n", f->name);
-        exit (0);
-    case 'o':
-        a->filename_ptm = arg;
-        break;
-    case 'v':
-        a->verbose = 1;
-        break;
-    case ARGP_KEY_ARG:
-        if (state->arg_num >= 1)
+    } else if (key == ARGP_KEY_ARG) {
+        if (state->arg_num > 0)
             argp_usage (state);
         a->filename_lp = arg;
-        break;
-    case ARGP_KEY_END:
-        if (state->arg_num < 1)
+    } else if (key == ARGP_KEY_END) {
+        if (state->arg_num == 0)
             argp_usage (state);
-        break;
-    default:
+    } else {
         return ARGP_ERR_UNKNOWN;
     }
     return 0;
@@ -94,73 +93,60 @@ int main (int argc, char *argv[]) {
     args.filename_ptm = "-";
     argp_parse (&argp, argc, argv, 0, 0, &args);
 
+    cli_select_devices ();
     double t0 = now_ms ();
 
+    /* 1. the light list, 2. one image header per entry (paths are relative to the .lp file) */
     FILE *fp_lp = fopen (args.filename_lp, "rb");
     if (fp_lp == NULL) {
         fprintf (stderr, "can't open %s\n", args.filename_lp);
         return 1;
     }
-    char *lp_copy = strdup (args.filename_lp);
-    const char *dir = dirname (lp_copy);
+    lp_entry_t *entries = NULL;
+    const size_t n = lp_read (fp_lp, 0, &entries);
+    fclose (fp_lp);
 
     ptm_header_t *header = ptm_alloc_header ();
     header->format = args.format;
-
-    size_t cap = 64, n = 0;
-    decoder_t **decoders = malloc (cap * sizeof (*decoders));
-    ptm_image_dims_t *all_dims = malloc (cap * sizeof (*all_dims));
+    decoder_t **decoders = malloc ((n ? n : 1) * sizeof (*decoders));
+    ptm_image_dims_t *all_dims = malloc ((n ? n : 1) * sizeof (*all_dims));
     ptm_image_dims_t dims0;
     memset (&dims0, 0, sizeof (dims0));
-
-    char *line = NULL;
-    size_t len = 0;
-    while (getline (&line, &len, fp_lp) != -1) {
-        char *name = malloc (len + 1);
-        float u = 0.0f, v = 0.0f, w = 0.0f;
-        if (sscanf (line, "%s %f %f %f", name, &u, &v, &w) >= 3) {
-            char *path = malloc (strlen (dir) + strlen (name) + 2);
-            sprintf (path, "%s/%s", dir, name);
-            FILE *fp = fopen (path, "rb");
-            if (fp == NULL) {
-                fprintf (stderr, "can't open %s\n", path);
-                return 1;
-            }
-            free (path);
-            ptm_image_dims_t dims;
-            if (ptm_codec_read_dims (fp, &dims)) {
-                fprintf (stderr, "can't read image header of %s\n", name);
-                return 1;
-            }
-            if (n == 0)
-                dims0 = dims;
-            if (dims.width != dims0.width || dims.height != dims0.height || dims.components != dims0.components) {
-                fprintf (stderr, "%s: all images must have the same size\n", name);   /* ref :238-243 asserts */
-                return 1;
-            }
-            decoder_t *d = calloc (1, sizeof (*d));
-            d->fp = fp;
-            d->filename = name;
-            d->u = u;
-            d->v = v;
-            d->w = w;
-            d->dinfo.output_width = dims.width;
-            d->dinfo.output_height = dims.height;
-            d->dinfo.output_components = (int) dims.components;
-            all_dims[n] = dims;
-            decoders[n++] = d;
-            if (n >= cap) {
-                cap *= 2;
-                decoders = realloc (decoders, cap * sizeof (*decoders));
-                all_dims = realloc (all_dims, cap * sizeof (*all_dims));
-            }
-        } else {
-            free (name);
+    char *lp_copy = strdup (args.filename_lp);
+    const char *dir = dirname (lp_copy);
+    for (size_t i = 0; i < n; ++i) {
+        char *path = malloc (strlen (dir) + strlen (entries[i].name) + 2);
+        sprintf (path, "%s/%s", dir, entries[i].name);
+        FILE *fp = fopen (path, "rb");
+        if (fp == NULL) {
+            fprintf (stderr, "can't open %s\n", path);
+            return 1;
         }
+        free (path);
+        if (ptm_codec_read_dims (fp, &all_dims[i])) {
+            fprintf (stderr, "can't read image header of %s\n", entries[i].name);
+            return 1;
+        }
+        if (i == 0)
+            dims0 = all_dims[0];
+        if (all_dims[i].width != dims0.width || all_dims[i].height != dims0.height ||
+            all_dims[i].components != dims0.components) {
+            fprintf (stderr, "%s: all images must have the same size\n", entries[i].name);   /* ref :238-243 asserts */
+            return 1;
+        }
+        decoder_t *d = calloc (1, sizeof (*d));
+        d->fp = fp;
+        d->filename = entries[i].name;
+        d->u = entries[i].u;
+        d->v = entries[i].v;
+        d->w = entries[i].w;
+        d->dinfo.output_width = all_dims[i].width;
+        d->dinfo.output_height = all_dims[i].height;
+        d->dinfo.output_components = (int) all_dims[i].components;
+        decoders[i] = d;
     }
-    free (line);
+    free (entries);
     free (lp_copy);
-    fclose (fp_lp);
 
     if (n < 12) {
         fprintf (stderr, "not enough jpegs %u < %d\n", (unsigned) n, 12);

@@ -20,6 +20,7 @@
 #include "../../../include/ptm_b200.h"
 #include "../../../include/ptmlib.h"
 #include "../ptm_codec.h"
+#include "cli_common.h"
 
 int main (int argc, char *argv[]) {
     if (argc != 4) {
@@ -27,6 +28,7 @@ int main (int argc, char *argv[]) {
         fprintf (stderr, "       Explodes a PTM into JPEGs\n");
         return 1;
     }
+    cli_select_devices ();
     FILE *fp = fopen (argv[1], "rb");
     if (fp == NULL) {
         fprintf (stderr, "can't open %s\n", argv[1]);
@@ -44,26 +46,16 @@ int main (int argc, char *argv[]) {
         fprintf (stderr, "can't open %s\n", argv[2]);
         return 1;
     }
-    size_t cap = 64, n = 0;
-    float *uv = malloc (cap * 2 * sizeof (float));
-    char *line = NULL;
-    size_t len = 0;
-    while (getline (&line, &len, fp_lp) != -1) {
-        char *name = malloc (len + 1);
-        float u = 0.0f, v = 0.0f;
-        if (sscanf (line, "%s %f %f", name, &u, &v) == 3) {
-            if (n == cap) {
-                cap *= 2;
-                uv = realloc (uv, cap * 2 * sizeof (float));
-            }
-            uv[2 * n] = u;
-            uv[2 * n + 1] = v;
-            ++n;
-        }
-        free (name);
-    }
-    free (line);
+    lp_entry_t *entries = NULL;
+    const size_t n = lp_read (fp_lp, 1, &entries);
     fclose (fp_lp);
+    float *uv = malloc ((n ? n : 1) * 2 * sizeof (float));
+    for (size_t i = 0; i < n; ++i) {
+        uv[2 * i] = entries[i].u;
+        uv[2 * i + 1] = entries[i].v;
+        free (entries[i].name);
+    }
+    free (entries);
 
     char *filename = malloc (strlen (argv[3]) + 20);
     strcpy (filename, argv[3]);

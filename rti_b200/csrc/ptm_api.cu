@@ -1,5 +1,6 @@
 // C ABI of libptm_b200.so (see include/ptm_b200.h).  Thin: argument checks,
 // context bookkeeping and launches; no arithmetic lives here.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -489,13 +490,39 @@ static int relight_common(ptmb_ctx_t *c, ptm::RelightArgs &a, bool lrgb, size_t 
     }
     CK(cudaMemcpyAsync(c->light_dev, c->light_host.data(), c->light_host.size() * sizeof(float),
                        cudaMemcpyHostToDevice, c->stream));
-    const unsigned kBatch = 1024;  // light table lives in shared memory
+    static int env_mode = -1;
+    if (env_mode < 0) {
+        const char *v = getenv("PTM_RELIGHT");
+        env_mode = !v ? PTMB_RELIGHT_AUTO : !strcmp(v, "exact") ? PTMB_RELIGHT_EXACT : !strcmp(v, "fast") ? PTMB_RELIGHT_FAST
+                                                                                                       : PTMB_RELIGHT_AUTO;
+    }
+    const int mode = c->relight_mode != PTMB_RELIGHT_AUTO ? c->relight_mode : env_mode;
+    // AUTO: a single direction is memory bound either way and stays bit-exact; batches take the tolerance kernels
+    const bool fast = mode == PTMB_RELIGHT_FAST || (mode == PTMB_RELIGHT_AUTO && n_dirs >= 4);
+    const unsigned kBatch = 960;  // light table lives in shared memory (48 bytes per direction in the packed kernels)
     for (unsigned d0 = 0; d0 < n_dirs; d0 += kBatch) {
         a.n_dirs = n_dirs - d0 < kBatch ? n_dirs - d0 : kBatch;
         a.light = c->light_dev + (size_t) d0 * PTMB_COEFFICIENTS;
         a.out = out_dev + (size_t) d0 * width * height * 3;
-        CK(ptm::launch_relight(a, lrgb, c->sm_count, c->stream));
+        for (int k = 0; k < 5; ++k)
+            a.lmax[k] = 0.f;
+        for (unsigned d = d0; d < d0 + a.n_dirs; ++d)
+            for (int k = 0; k < 5; ++k) {
+                const float l = fabsf(c->light_host[(size_t) d * PTMB_COEFFICIENTS + k]);
+                a.lmax[k] = l > a.lmax[k] || l != l ? l : a.lmax[k];   // a NaN direction makes every pixel take the clamped loop
+            }
+        cudaError_t e = fast ? ptm::launch_relight_fast(a, lrgb, c->sm_count, c->stream) : cudaErrorNotSupported;
+        if (e == cudaErrorNotSupported)
+            e = ptm::launch_relight(a, lrgb, c->sm_count, c->stream);
+        CK(e);
     }
+    return 0;
+}
+
+int ptmb_set_relight_mode(ptmb_ctx_t *c, int mode) {
+    REQUIRE(c, "ctx is NULL");
+    REQUIRE(mode >= PTMB_RELIGHT_AUTO && mode <= PTMB_RELIGHT_FAST, "unknown relight mode");
+    c->relight_mode = mode;
     return 0;
 }
 

@@ -380,9 +380,36 @@ cudaError_t launch_keys_init(int *keys, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// The pinv table of the non-streaming kernels lives in dynamic shared memory: 24 (generic) or 32 (register
+// kernels) bytes per light, i.e. up to 64 KB at the 2048 lights ptmb_set_matrix accepts -- above the 48 KB a
+// launch may use without opting in.  Attributes are per device, hence the per-device flag.
+static cudaError_t allow_large_tables() {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess || dev < 0 || dev >= 64 || done[dev])
+        return e;
+    const int bytes = 2048 * 2 * (int) sizeof(float4);
+#define PTM_ALLOW(k)                                                                         \
+    if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) \
+        return e;
+    PTM_ALLOW(fit_lrgb_generic_kernel<uint8_t>)
+    PTM_ALLOW(fit_lrgb_generic_kernel<uint16_t>)
+    PTM_ALLOW(fit_rgb_generic_kernel<uint8_t>)
+    PTM_ALLOW(fit_rgb_generic_kernel<uint16_t>)
+    PTM_ALLOW(fit_lrgb_u8_kernel<true>)
+    PTM_ALLOW(fit_lrgb_u8_kernel<false>)
+    PTM_ALLOW(fit_rgb_u8_kernel)
+#undef PTM_ALLOW
+    done[dev] = true;
+    return cudaSuccess;
+}
+
 cudaError_t launch_fit_lrgb(const FitArgs &a, int sample_type, int sm_count, cudaStream_t st) {
     if (a.pixels == 0)
         return cudaSuccess;
+    if (cudaError_t ea = allow_large_tables())
+        return ea;
     if (sample_type != 0 && sample_type != 1)
         return cudaErrorInvalidValue;
     const size_t gen_smem = (size_t) a.n_lights * PTM_NCOEF * sizeof(float);
@@ -435,6 +462,8 @@ cudaError_t launch_fit_lrgb(const FitArgs &a, int sample_type, int sm_count, cud
 cudaError_t launch_fit_rgb(const FitArgs &a, int sample_type, int sm_count, cudaStream_t st) {
     if (a.pixels == 0)
         return cudaSuccess;
+    if (cudaError_t ea = allow_large_tables())
+        return ea;
     const size_t gen_smem = (size_t) a.n_lights * PTM_NCOEF * sizeof(float);
     if (sample_type == 1) {   // 16-bit stacks: streaming kernel over the tiles, generic kernel for the rest
         size_t done16 = 0;

@@ -48,6 +48,7 @@ struct ptmb_ctx {
     float digit_scale[6] = {0, 0, 0, 0, 0, 0};
     unsigned kpad = 0;
     int engine = 0;
+    int relight_mode = 0;                    // PTMB_RELIGHT_*
     int *keys_dev = nullptr;                 // scratch for the host-buffer entry points
     ptmb_scale_bias_t *sb_dev = nullptr;
     std::vector<float> light_host;

@@ -30,6 +30,7 @@ struct Jpeg {
     nvjpegJpegState_t state = nullptr;
     nvjpegEncoderState_t enc_state = nullptr;
     nvjpegEncoderParams_t enc_params = nullptr;
+    cudaStream_t enc_stream = nullptr;   // the stream the encoder objects were created against
     bool ok = false;
 };
 
@@ -75,11 +76,22 @@ int jpeg_for(ptmb_ctx_t *c, Jpeg **out) {
     if (c->device < 0 || c->device >= 64)
         return ptmb_internal_fail("jpeg", "device index out of range");
     Jpeg &j = g_jpeg[c->device];
-    if (!j.ok) {
+    if (!j.handle) {
         NJ(nvjpegCreateSimple(&j.handle));
         NJ(nvjpegJpegStateCreate(j.handle, &j.state));
+    }
+    if (!j.ok || j.enc_stream != c->stream) {
+        // the encoder objects are tied to the stream they were created against: a context whose stream
+        // changed (ptmb_set_stream), or a second context on this GPU, gets fresh ones
+        if (j.ok) {
+            CJ(cudaStreamSynchronize(j.enc_stream));
+            nvjpegEncoderParamsDestroy(j.enc_params);
+            nvjpegEncoderStateDestroy(j.enc_state);
+            j.ok = false;
+        }
         NJ(nvjpegEncoderStateCreate(j.handle, &j.enc_state, c->stream));
         NJ(nvjpegEncoderParamsCreate(j.handle, &j.enc_params, c->stream));
+        j.enc_stream = c->stream;
         j.ok = true;
     }
     *out = &j;

@@ -70,6 +70,7 @@ struct RelightArgs {
     const float *light;       // device [n_dirs][6]: u^2 v^2 uv u v 1
     unsigned n_dirs;
     uint8_t *out;             // [n_dirs][height][width][3]
+    float lmax[5];            // max over the batch of |u^2| |v^2| |uv| |u| |v| (range check of the tolerance kernels)
 };
 
 bool pack_mma_digits(const float *M, unsigned n_lights, std::vector<int8_t> &image, float *scale, unsigned *kpad_out);
@@ -98,6 +99,8 @@ cudaError_t launch_minmax(const float *coeffs, size_t pixels, int *keys, int sm_
 cudaError_t launch_quantise(const float *coeffs, size_t pixels, const KeySource &src, uint8_t *bytes, void *sb,
                             bool consume, int sm_count, cudaStream_t st);
 cudaError_t launch_relight(const RelightArgs &a, bool lrgb, int sm_count, cudaStream_t st);
+// tolerance form (ptm_relight_fast.cu); cudaErrorNotSupported = layout not taken, use launch_relight
+cudaError_t launch_relight_fast(const RelightArgs &a, bool lrgb, int sm_count, cudaStream_t st);
 cudaError_t launch_div255_selftest(unsigned long long first, unsigned long long count,
                                    unsigned long long *mismatches_dev, int sm_count, cudaStream_t st);
 cudaError_t launch_synth(uint32_t seed, int mode, int sample_type, uint32_t pixel0, size_t pixels,

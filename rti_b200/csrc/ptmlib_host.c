@@ -58,19 +58,18 @@ static void gpu_die (const char *what) {
 
 static ptmb_ctx_t *gpu (void) {
     if (!g_ctx) {
-        /* PTM_B200_DEVICE selects the GPU (default 0).  A one-shot command line pays for CUDA
-         * start-up on every run, and the driver initialises every visible GPU (about 1 s on an
-         * 8-GPU box): unless the user already restricted visibility, expose only the chosen one. */
+        /* PTM_B200_DEVICE selects the GPU (default 0); the ordinal is passed on unchanged and the
+         * process environment is left alone (a library must not narrow CUDA_VISIBLE_DEVICES under a
+         * host that also runs torch / NCCL -- the command-line mains do that for themselves, before
+         * their first CUDA call, see cli/cli_common.h). */
         const char *dev = getenv ("PTM_B200_DEVICE");
-        int ordinal = dev ? atoi (dev) : 0;
-        if (!getenv ("CUDA_VISIBLE_DEVICES")) {
-            char buf[16];
-            snprintf (buf, sizeof (buf), "%d", ordinal);
-            setenv ("CUDA_VISIBLE_DEVICES", buf, 1);
-            ordinal = 0;
-        }
+        const int ordinal = dev ? atoi (dev) : 0;
         if (ptmb_create (ordinal, NULL, &g_ctx))
             gpu_die ("ptmb_create");
+        /* the drop-in reproduces the reference decoder's rasters byte for byte unless told otherwise
+         * (PTM_RELIGHT=fast: every byte within +-1, sweeps at the memory rate) */
+        if (!getenv ("PTM_RELIGHT"))
+            ptmb_set_relight_mode (g_ctx, PTMB_RELIGHT_EXACT);
     }
     return g_ctx;
 }
@@ -133,18 +132,21 @@ static void put_floats (FILE *fp, int n, const float *v) {
     fputc ('\n', fp);
 }
 
-/* numbers are read with a trailing blank in the format, which also swallows the newline
- * (and any further white space) before the block payload -- same as ref :120-136 */
+/* Numbers are read WITHOUT the reference's trailing blank in the format ("%d ", ref :120-136): that
+ * blank swallows every white-space byte after the last header field, i.e. also leading payload bytes
+ * 0x09-0x0D / 0x20 of an uncompressed block or stream -- ordinary coefficient values -- and shifts the
+ * whole payload.  Each conversion skips the white space in front of it, and header_end() consumes the
+ * one line end that terminates the header (deliberate deviation from the reference). */
 static void get_ints (FILE *fp, int n, int *v) {
     for (int i = 0; i < n; ++i)
-        if (fscanf (fp, "%d ", v + i) != 1)
+        if (fscanf (fp, "%d", v + i) != 1)
             v[i] = 0;
 }
 
 static void get_sizes (FILE *fp, int n, size_t *v) {
     for (int i = 0; i < n; ++i) {
         unsigned long t = 0;
-        if (fscanf (fp, "%lu ", &t) != 1)
+        if (fscanf (fp, "%lu", &t) != 1)
             t = 0;
         v[i] = t;
     }
@@ -152,8 +154,17 @@ static void get_sizes (FILE *fp, int n, size_t *v) {
 
 static void get_floats (FILE *fp, int n, float *v) {
     for (int i = 0; i < n; ++i)
-        if (fscanf (fp, "%f ", v + i) != 1)
+        if (fscanf (fp, "%f", v + i) != 1)
             v[i] = 0.0f;
+}
+
+/* blanks up to and including exactly one '\n' (the writers end every header line with one) */
+static void header_end (FILE *fp) {
+    int ch;
+    while ((ch = fgetc (fp)) == ' ' || ch == '\t' || ch == '\r')
+        ;
+    if (ch != '\n' && ch != EOF)
+        ungetc (ch, fp);
 }
 
 static char *read_trimmed_line (FILE *fp) {
@@ -205,6 +216,7 @@ ptm_header_t *ptm_read_header (FILE *fp) {
     } else {
         h->compression_param[0] = 90;   /* ref :211 -- quality used when relit images are written */
     }
+    header_end (fp);
     return h;
 }
 

@@ -91,6 +91,12 @@ class Context:
         code = {"default": 0, "ffma": 1, "mma": 2}[engine] if isinstance(engine, str) else int(engine)
         _lib.check(self._lib.ptmb_set_fit_engine(self._h, code))
 
+    def set_relight_mode(self, mode):
+        """"auto" (exact below 4 directions, else fast) | "exact" (bit-identical to the reference decoder) |
+        "fast" (every byte within +-1, HBM-rate sweeps)."""
+        code = {"auto": 0, "exact": 1, "fast": 2}[mode] if isinstance(mode, str) else int(mode)
+        _lib.check(self._lib.ptmb_set_relight_mode(self._h, code))
+
     def mma_launches(self):
         return int(self._lib.ptmb_mma_launches())
 

@@ -102,6 +102,9 @@ class PtmEncoder:
         self.launches_per_encode = 2 if (self.planes == 1 and self.exchange_kind in ("none", "p2p")) else 3
 
     def _use_current_stream(self):
+        """Work is enqueued on torch's CURRENT stream of the encoder's device at the time of each call (not
+        the one that was current at construction), so it is ordered against the producer of `stack` and
+        the consumers of the results."""
         self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
     def fit(self, stack):
@@ -109,6 +112,7 @@ class PtmEncoder:
         [n_lights, rows, width, 3], contiguous per light; lights may be strided (a row range of a
         larger stack), which is how a slab of a resident image is passed without a copy."""
         assert stack.is_cuda and stack.dim() == 4 and stack[0].is_contiguous()
+        self._use_current_stream()
         n = stack.shape[0]
         assert n == self.n_lights and stack[0].numel() == self.pixels * 3
         st = {torch.uint8: U8, torch.uint16: U16}[stack.dtype]
@@ -120,6 +124,7 @@ class PtmEncoder:
             self.ctx.fit_rgb(stack, image_stride, self.pixels, self.coeffs, self.pixels * NCOEF, self.keys, st)
 
     def exchange(self):
+        self._use_current_stream()
         if self.xchg is not None:
             self.xchg.allreduce_max(self.keys)
         else:
@@ -129,6 +134,7 @@ class PtmEncoder:
         """K2: scale/bias from the (global) keys, then bytes for every plane.  The planes are contiguous
         and share one scale/bias (rti-builder/ptmlib.c:867-880), so the RGB formats are one launch over
         planes * pixels coefficient vectors."""
+        self._use_current_stream()
         self.ctx.quantise(self.coeffs, self.pixels * self.planes, self.keys, self.coef_bytes, self.sb,
                           consume=not self.keep_coeffs)
 
@@ -137,6 +143,7 @@ class PtmEncoder:
         two-launch entry (ptmb_encode_lrgb_dev); self.keys is not updated on that path."""
         if self.planes == 1 and self.exchange_kind in ("none", "p2p"):
             assert stack.is_cuda and stack.is_contiguous() and stack.shape[0] == self.n_lights
+            self._use_current_stream()
             st = {torch.uint8: U8, torch.uint16: U16}[stack.dtype]
             self.ctx.encode_lrgb_dev(stack, self.pixels * 3 * stack.element_size(), self.pixels, self.coeffs,
                                      self.rgb, self.coef_bytes, self.sb, xchg=self.xchg, sample_type=st)
@@ -164,7 +171,11 @@ class PtmRelighter:
         self.width, self.height = int(width), int(height)
         self.ctx = Context(self.device.index, stream=torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _use_current_stream(self):
+        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
     def relight_lrgb(self, coef, rgb, scale, bias, uv, out=None):
+        self._use_current_stream()
         uv = np.asarray(uv, dtype=np.float32).reshape(-1, 2)
         if out is None:
             out = torch.empty((uv.shape[0], self.height, self.width, 3), dtype=torch.uint8, device=self.device)
@@ -172,6 +183,7 @@ class PtmRelighter:
         return out
 
     def relight_rgb(self, r, g, b, scale, bias, uv, out=None):
+        self._use_current_stream()
         uv = np.asarray(uv, dtype=np.float32).reshape(-1, 2)
         if out is None:
             out = torch.empty((uv.shape[0], self.height, self.width, 3), dtype=torch.uint8, device=self.device)

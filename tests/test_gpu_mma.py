@@ -7,6 +7,7 @@ coefficient bytes +-1 LSB on summation-order ties only.
 import numpy as np
 import pytest
 
+from conftest import assert_byte_parity
 from test_gpu_parity import assert_bytes_close, coeff_error, dev, gpu_encode_lrgb, gpu_encode_rgb
 
 pytestmark = pytest.mark.gpu
@@ -65,9 +66,7 @@ def test_rgb_mma_vs_oracle(ctx, oracle, dome1, M60, W, H):
         assert err <= 1e-5
     np.testing.assert_allclose(got["minmax"], want["minmax"], rtol=2e-6, atol=1e-4)
     np.testing.assert_allclose(got["scale"], want["scale"], rtol=2e-6)
-    assert np.abs(got["bias"].astype(int) - want["bias"].astype(int)).max() <= 1
-    if np.array_equal(got["bias"], want["bias"]):
-        assert_bytes_close(got["coef"], want["coef"], "RGB coefficient bytes (mma) %dx%d" % (W, H), 0.02)
+    assert_byte_parity(got["coef"], want["coef"], got["bias"], want["bias"], "RGB coefficient bytes (mma) %dx%d" % (W, H))
 
 
 @pytest.mark.parametrize("W,H", SHAPES)
@@ -85,9 +84,7 @@ def test_lrgb_mma_vs_oracle(ctx, oracle, dome1, M60, W, H):
     # scale = (max - min) / 256: the two extrema carry the ORACLE's summation-order noise (a few ulp of
     # the coefficient scale, which is larger than the range on small images); the engine itself rounds once
     np.testing.assert_allclose(got["scale"], want["scale"], rtol=5e-6)
-    assert np.abs(got["bias"].astype(int) - want["bias"].astype(int)).max() <= 1
-    if np.array_equal(got["bias"], want["bias"]):
-        assert_bytes_close(got["coef"], want["coef"], "LRGB coefficient bytes (mma) %dx%d" % (W, H), 0.02)
+    assert_byte_parity(got["coef"], want["coef"], got["bias"], want["bias"], "LRGB coefficient bytes (mma) %dx%d" % (W, H))
 
 
 @pytest.mark.parametrize("n", [6, 8, 12, 32, 33, 100, 128, 160, 192, 224])
@@ -152,11 +149,8 @@ def test_mma_matches_ffma_engine_at_scale(ctx, ctx_ffma, oracle, dome1, M60):
     print("max |mma - ffma| per coefficient, relative to its range:", d / scale)
     assert (d <= 1e-5 * scale).all()
     np.testing.assert_allclose(outs[0][3][:6].view(np.float32), outs[1][3][:6].view(np.float32), rtol=5e-6)
-    if np.array_equal(outs[0][3][6:], outs[1][3][6:]):
-        diff = (outs[0][2].to(torch.int16) - outs[1][2].to(torch.int16)).abs()
-        assert int(diff.max()) <= 1
-        print("bytes differing between engines: %d of %d" % (int((diff != 0).sum()), diff.numel()))
-        assert int((diff != 0).sum()) <= 0.01 * diff.numel()
+    assert_byte_parity(outs[0][2].cpu().numpy(), outs[1][2].cpu().numpy(), outs[0][3][6:], outs[1][3][6:],
+                       "bytes between engines", 0.01)
 
 
 @pytest.mark.parametrize("W,H,n", [(64, 1, 60), (80, 33, 60), (72, 33, 100), (512, 150, 100), (48, 5, 224)])
