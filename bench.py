@@ -2,24 +2,34 @@
 """Benchmark of the PTM fit hot path (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # B200 arm (torchrun for N > 1)
-    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path, same workload
 
 A step is one LRGB PTM fit of a 24 MP (6000 x 4000) x 60-light (dome1.lp) uint8 stack:
-keys-init -> K1 (fit + chroma + colour/normalise + extrema) -> [int32 MAX all-reduce of the
-12 extrema keys when N > 1] -> K2 (scale/bias + quantise).  For N > 1 the SAME 24 MP image is
-row-sharded over the ranks (BASELINE.json configs[2]) -- strong scaling.
+K1 (fit + chroma + colour/normalise + extrema) -> hand-off of the 12 extrema keys (to every
+GPU's mailbox over NVLink when N > 1) -> K2 (scale/bias + quantise).  For N > 1 the SAME 24 MP
+image is row-sharded over the ranks (BASELINE.json configs[2]) -- strong scaling.
 
-value   = pixels / device time, stack already resident in HBM (CUDA events, max over ranks)
-e2e     = the same through the host-buffer C-ABI call (ptmb_encode_host_*): pinned host
-          stack -> H2D -> K1 -> exchange -> K2 -> D2H of the blocks, all inside the timed region
-roofline= K1 (dominant kernel) against the measured HBM peak, timed live with CUDA events
-cpu_baseline = the reference's own CPU functions on this box's host cores (bounded sample)
+value        pixels / device time, stack already resident in HBM (CUDA events, max over ranks)
+e2e          the same through the host-buffer C-ABI call (ptmb_encode_host_*): pinned host stack
+             -> H2D -> K1 -> exchange -> K2 -> D2H of the blocks, all inside the timed region;
+             next to it the measured pinned H2D rate of the same buffers (all ranks at once)
+e2e_dropin   (N = 1) the reference's OWN call sequence through libptm.so (ptm_fit_poly_jsample,
+             ptm_cbcr_avg, colour loop, ptm_scale_coefficients) on pageable host memory
+roofline     the whole fit path on SURVEY.md 8(d)'s 189 algorithmic bytes per pixel against the
+             measured HBM peak; K1 (dominant kernel) timed live with CUDA events beside it
+parity       (N = 1) every byte of the GPU blocks against the reference's CPU result for the same
+             24 MP stack; (N > 1) every rank's sharded blocks against a single-GPU encode of the
+             whole image made on that rank
+extra        (N = 1) BASELINE.json configs[3] / configs[4]: 50 MP x 100 x 16-bit LRGB and RGB
+             encodes, the 24 MP RGB-format encode, 360-direction relight sweeps
+cpu_baseline the reference's own CPU functions on this box's host cores, whole 24 MP image
 
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -34,6 +44,7 @@ sys.path.insert(0, ROOT)
 WIDTH, HEIGHT, N_LIGHTS = 6000, 4000, 60
 SEED = 0x5EED0001
 METRIC = "PTM fit Mpixel/s at 24MP x dome1.lp lights (LRGB, uint8)"
+WORKLOAD = "%.0fMP (%dx%d) x %d lights dome1.lp, LRGB uint8"
 ALG_BYTES_PATH = N_LIGHTS * 3 + 6 + 3          # 189 B/px: SURVEY.md 8(d), whole fit path
 ALG_BYTES_K1 = N_LIGHTS * 3 + 24 + 3           # 207 B/px: K1's own compulsory input + output
 FALLBACK_HBM_GBS = 6650.0                      # /opt/skills/guides/B200_PROFILING.md
@@ -45,12 +56,17 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--driver", default="torchrun", choices=["torchrun", "c"],
+                    help="N > 1: one process per GPU (torchrun), or ONE process driving all GPUs through the "
+                         "C ABI's multi-GPU entry (ptmb_multi_*; launch with plain `python bench.py --gpus N --driver c`)")
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline passes")
     return ap.parse_args()
 
 
@@ -62,6 +78,35 @@ def measured_peak():
         except Exception:
             pass
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def kernel_sources_sha256():
+    """Hash of the CUDA sources the shipped library was built from; profiles/traffic.json records the hash of the
+    sources its ncu capture was taken with, so a stale capture is reported as such instead of being quoted."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "rti_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh")) or name in ("ptm_kernels.h", "ptm_internal.h"):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()
+
+
+def read_traffic(kernels):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum from an `ncu --set full` capture of
+    this bench command) for the named kernels, or (None, why)."""
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(tpath))
+    except Exception:
+        return None, "profiles/traffic.json missing"
+    if t.get("kernel_sources_sha256") != kernel_sources_sha256():
+        return None, "profiles/traffic.json was captured with other kernel sources (stale)"
+    try:
+        per = {k: float(t[k]["dram_bytes_read"]) + float(t[k]["dram_bytes_write"]) for k in kernels}
+    except Exception:
+        return None, "profiles/traffic.json lacks " + ", ".join(kernels)
+    return per, t.get("source", "profiles/traffic.json")
 
 
 # --------------------------------------------------------------------- clocks
@@ -110,17 +155,24 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def bind_to_gpu_numa_node(index):
-    """Pin this process to the CPU cores NVML reports as local to the GPU, so that the pinned host
-    buffers of the e2e leg are first-touched on the GPU's NUMA node (matters with one rank per GPU)."""
+def gpu_cpu_affinity(index):
+    """CPU cores NVML reports as local to the GPU (its NUMA node), or an empty set."""
     try:
         import pynvml as nv
         nv.nvmlInit()
         h = nv.nvmlDeviceGetHandleByIndex(index)
         n_words = (os.cpu_count() + 63) // 64
         mask = nv.nvmlDeviceGetCpuAffinity(h, n_words)
-        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
-        cpus &= set(os.sched_getaffinity(0))
+        return {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+    except Exception:
+        return set()
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPU cores local to the GPU BEFORE any pinned host buffer is allocated, so that the
+    buffers of the e2e leg are first-touched on the GPU's NUMA node (matters with one rank per GPU)."""
+    try:
+        cpus = gpu_cpu_affinity(index) & set(os.sched_getaffinity(0))
         if cpus:
             os.sched_setaffinity(0, cpus)
             return len(cpus)
@@ -141,32 +193,33 @@ def physical_gpu_index(local):
 
 # ------------------------------------------------------------------- CPU legs
 
-def host_sample_stack(width, rows, lights):
-    from oracle import oracle as O
-    return O.synth_stack(SEED, 0, width, rows, lights, row0=0, rows=rows)
+def reference_pass(O, stack, M, threads):
+    dt, kind, res = O.cpu_encode_lrgb_timed(stack, M, threads=threads)
+    return dt, kind, res
 
 
-def cpu_baseline(width, lights, M, target_seconds):
-    """Reference CPU sequence on a bounded row slab of the same workload, repeated until about
-    `target_seconds` of CPU wall time have been spent."""
+def cpu_baseline(stack_np, lights, M, target_seconds):
+    """The reference's CPU sequence over the WHOLE image of this workload on all host cores, repeated until about
+    `target_seconds` have been spent.  Returns (cpu_baseline object, the reference result of the last pass)."""
     from oracle import oracle as O
-    cores = os.cpu_count() or 1
-    rows = 1200                                              # 7.2 MP slab: 1.3 GB of host memory
-    st = host_sample_stack(width, rows, lights)
-    O.cpu_encode_lrgb_timed(st[:, :16], M, threads=cores)    # warm-up (thread pools, page faults)
-    total, passes, kind = 0.0, 0, "port"
-    while total < target_seconds and passes < 200:
-        dt, kind, _ = O.cpu_encode_lrgb_timed(st, M, threads=cores)
+    cores = O.set_threads(O.host_cores())
+    n, H, W, _ = stack_np.shape
+    reference_pass(O, stack_np[:, :16], M, cores)           # warm-up (thread pools, page faults)
+    total, passes, kind, res = 0.0, 0, "port", None
+    while passes < 1 or (total < target_seconds and passes < 200):
+        dt, kind, res = reference_pass(O, stack_np, M, cores)
         total += dt
         passes += 1
-    return {"value": width * rows * passes / total / 1e6, "unit": "Mpixel/s", "cores": cores, "kind": kind,
-            "sample": "%d passes over %d rows x %d px x %d lights of the same synthetic stack, %.1f s in total; "
-                      "OpenBLAS %s, OMP threads = cores" % (passes, rows, width, len(lights), total,
-                                                            O.lib().orc_blas_corename().decode())}
+    return {"value": W * H * passes / total / 1e6, "unit": "Mpixel/s", "cores": cores, "kind": kind,
+            "sample": "%d pass(es) over the whole %d x %d x %d-light stack (same bytes as the GPU run), %.1f s in "
+                      "total; OpenBLAS %s, OMP threads = %d" % (passes, W, H, n, total,
+                                                                O.lib().orc_blas_corename().decode(), cores)}, res
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation, all host threads."""
+    """--impl reference: the reference's own CPU implementation on ALL host cores, one whole 24 MP stack per step
+    (same workload as the B200 arm).  Under torchrun rank 0 alone runs; the launcher's OMP_NUM_THREADS=1 is
+    overridden through the OpenMP runtime itself."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -174,28 +227,206 @@ def run_reference(args):
     from rti_b200 import lights as LS
     L = LS.dome1_lights()
     M = O.pinv(L)
-    cores = os.cpu_count() or 1
-    rows = 200                                                # 1.2 MP per step: seconds, not minutes
-    st = host_sample_stack(args.width, rows, L)
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))   # undo any launcher pinning
+    except Exception:
+        pass
+    cores = O.set_threads(O.host_cores())
+    W, H = args.width, args.height
+    st = O.synth_stack(SEED, 0, W, H, L)
     kind = "port"
-    for _ in range(max(1, args.warmup)):
-        _, kind, _ = O.cpu_encode_lrgb_timed(st, M, threads=cores)
+    for _ in range(max(1, min(args.warmup, 2))):
+        _, kind, _ = reference_pass(O, st, M, cores)
     t = 0.0
     for _ in range(args.steps):
-        dt, kind, _ = O.cpu_encode_lrgb_timed(st, M, threads=cores)
+        dt, kind, _ = reference_pass(O, st, M, cores)
         t += dt
-    value = args.width * rows * args.steps / t / 1e6
-    sample = "%d rows x %d px x %d lights per step (bounded sample of the 24 MP workload)" % (rows, args.width, len(L))
+    value = W * H * args.steps / t / 1e6
+    sample = "the whole %d x %d x %d-light stack per step (same workload as the B200 arm), %d OMP threads, OpenBLAS %s" % (
+        W, H, len(L), cores, O.lib().orc_blas_corename().decode())
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "steps": args.steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "24MP (6000x4000) x 60 lights dome1.lp, LRGB uint8 -- CPU on a bounded sample",
-                   "sample": sample},
+        "config": {"workload": WORKLOAD % (W * H / 1e6, W, H, N_LIGHTS), "arm": "reference CPU path, whole image per step"},
         "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+# ------------------------------------------------------------------- parity
+
+def parity_vs_reference(enc, ref, M, stack_np):
+    """Every byte of the device-resident result against the reference's CPU result for the same stack
+    (SURVEY.md 8(d) "parity gates run with every measurement")."""
+    import torch
+    H, W = ref["coef"].shape[:2]
+    got_coef = enc.coef_bytes[0].cpu().numpy().reshape(H, W, 6)
+    got_rgb = enc.rgb.cpu().numpy().reshape(H, W, 3)
+    scale, bias = enc.scale_bias()
+    d = np.abs(got_coef.astype(np.int16) - ref["coef"].astype(np.int16))
+    # float coefficients: |delta| relative to the coefficient's scale sum_n |M_kn| y_n * 256 / mean(y) (SURVEY 7.2)
+    rows = np.linspace(0, H - 1, 16).astype(int)
+    got_f = enc.coeffs[0].reshape(H, W, 6)[torch.from_numpy(rows).cuda()].cpu().numpy()
+    y = stack_np[:, rows, :, 0].astype(np.float64)
+    bound = np.einsum("kn,nrw->rwk", np.abs(M).astype(np.float64), y) * (256.0 / np.maximum(np.floor(y.sum(0) / y.shape[0]), 1.0))[..., None]
+    rel = float((np.abs(got_f.astype(np.float64) - ref["coeffs"][rows].astype(np.float64)) / np.maximum(bound, 1e-30)).max())
+    out = {
+        "against": "reference CPU result, whole image (%d x %d)" % (W, H),
+        "coef_bytes_differing": int((d != 0).sum()), "coef_bytes_total": int(d.size), "max_abs": int(d.max()),
+        "rgb_identical": bool(np.array_equal(got_rgb, ref["rgb"])),
+        "scale_rel": float(np.max(np.abs(scale - ref["scale"]) / np.abs(ref["scale"]))),
+        "bias_delta": int(np.max(np.abs(bias.astype(np.int64) - ref["bias"].astype(np.int64)))),
+        "coeff_rel_err_16_rows": rel,
+    }
+    out["ok"] = bool(out["max_abs"] <= (2 if out["bias_delta"] else 1) and out["rgb_identical"] and
+                     out["bias_delta"] <= 1 and out["scale_rel"] <= 1e-5 and rel <= 1e-5)
+    return out
+
+
+def sharded_identity(enc, M, L, W, H, r0, r1, world):
+    """This rank's sharded blocks against ITS OWN single-GPU encode of the whole image: byte-identical or not."""
+    import torch
+    import torch.distributed as dist
+    from rti_b200.device import U8, light_q14
+    from rti_b200.encoder import PtmEncoder
+    P = W * H
+    full = torch.empty((N_LIGHTS, H, W, 3), dtype=torch.uint8, device="cuda")
+    single = PtmEncoder(W, H, M, planes=1, exchange="none", group=None, single=True)
+    single.ctx.synth(SEED, 0, U8, 0, P, light_q14(L), full, P * 3)
+    single.encode(full)
+    torch.cuda.synchronize()
+    same = (torch.equal(single.coef_bytes[0][r0 * W:r1 * W], enc.coef_bytes[0]) and
+            torch.equal(single.rgb[r0 * W:r1 * W], enc.rgb) and torch.equal(single.sb, enc.sb))
+    digest = hashlib.sha256(single.coef_bytes[0].cpu().numpy().tobytes() + single.rgb.cpu().numpy().tobytes()).hexdigest()
+    flag = torch.tensor([1 if same else 0], dtype=torch.int32, device="cuda")
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    del full, single
+    torch.cuda.empty_cache()
+    return bool(flag.item()), digest
+
+
+# ------------------------------------------------------------------- extras (configs[3], configs[4])
+
+def timed_ms(fn, reps, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def run_extras(M60, L60, peak, gpu_index):
+    """BASELINE.json configs[3] (50 MP x 100 lights x 16 bit, LRGB + RGB format) and configs[4] (360-direction
+    relight sweep over a 24 MP PTM), plus the 24 MP RGB-format encode; a few steps each, clocks sampled."""
+    import torch
+    from rti_b200 import lights as LS
+    from rti_b200.device import U8, U16, light_q14
+    from rti_b200.encoder import PtmEncoder, PtmRelighter
+    from rti_b200.ptmlib import ptm_svd
+    out = []
+
+    def record(name, fn, reps, units, alg_bytes, unit_name, **more):
+        s = ClockSampler(gpu_index)
+        s.start()
+        ms = timed_ms(fn, reps)
+        clocks = s.stop()
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        out.append(dict({"config": name, "ms": ms, "steps": reps, "value": units / (ms * 1e-3) / 1e6,
+                         "unit": unit_name, "algorithmic_bytes": alg_bytes, "achieved_gbs": gbs,
+                         "frac_of_hbm_peak": gbs / peak, "clocks": clocks}, **more))
+
+    def encode_case(name, W, H, L, dtype, planes, mode, reps):
+        st, td = (U8, torch.uint8) if dtype == "u8" else (U16, torch.uint16)
+        n, P = len(L), W * H
+        M = ptm_svd(L)
+        stack = torch.empty((n, H, W, 3), dtype=td, device="cuda")
+        enc = PtmEncoder(W, H, M, planes=planes)
+        enc.ctx.synth(SEED, mode, st, 0, P, light_q14(L), stack, P * 3 * stack.element_size())
+        bpp = n * 3 * stack.element_size() + (18 if planes == 3 else 9)
+        record(name, lambda: enc.encode(stack), reps, P, P * bpp, "Mpixel/s", algorithmic_bytes_per_px=bpp,
+               l2="stack larger than L2, streamed once per step")
+        return enc, stack
+
+    # configs[3]: 8688 x 5792 = 50.3 MP, 100 lights, 16-bit linear samples
+    L100 = LS.dome100_lights()
+    for name, planes, mode in (("C4 LRGB u16, 50.3MP x 100 lights", 1, 0), ("C4 RGB-format u16, 50.3MP x 100 lights", 3, 1)):
+        enc, stack = encode_case(name, 8688, 5792, L100, "u16", planes, mode, 3)
+        del enc, stack
+        torch.cuda.empty_cache()
+    enc, stack = encode_case("RGB-format u8, 24MP x 60 lights", WIDTH, HEIGHT, L60, "u8", 3, 1, 5)
+    del stack
+    # configs[4]: 360 directions on a ring of radius 0.7; RGB-format PTM first (its blocks are at hand)
+    W, H = WIDTH, HEIGHT
+    P = W * H
+    D = 360
+    th = np.deg2rad(np.arange(D) * 360.0 / D)
+    uv = np.stack([0.7 * np.cos(th), 0.7 * np.sin(th)], 1).astype(np.float32)
+    rel = PtmRelighter(W, H)
+    rasters = torch.empty((D, H, W, 3), dtype=torch.uint8, device="cuda")
+    scale, bias = enc.scale_bias()
+    cb = enc.coef_bytes
+    for mode in ("fast", "exact"):
+        rel.ctx.set_relight_mode(mode)
+        record("C5 relight sweep, RGB-format 24MP PTM x 360 directions (%s)" % mode,
+               lambda: rel.relight_rgb(cb[0], cb[1], cb[2], scale, bias, uv, rasters), 2, P * D, P * (18 + 3 * D),
+               "Mpixel-directions/s", tolerance="+-1 per byte" if mode == "fast" else "bit-exact",
+               l2="26 GB of rasters written per step")
+    del enc, cb
+    torch.cuda.empty_cache()
+    stack = torch.empty((N_LIGHTS, H, W, 3), dtype=torch.uint8, device="cuda")
+    enc = PtmEncoder(W, H, M60, planes=1)
+    enc.ctx.synth(SEED, 0, U8, 0, P, light_q14(L60), stack, P * 3)
+    enc.encode(stack)
+    torch.cuda.synchronize()
+    del stack
+    scale, bias = enc.scale_bias()
+    for mode in ("fast", "exact"):
+        rel.ctx.set_relight_mode(mode)
+        record("C5 relight sweep, LRGB 24MP PTM x 360 directions (%s)" % mode,
+               lambda: rel.relight_lrgb(enc.coef_bytes[0], enc.rgb, scale, bias, uv, rasters), 2, P * D,
+               P * (9 + 3 * D), "Mpixel-directions/s", tolerance="+-1 per byte" if mode == "fast" else "bit-exact",
+               l2="26 GB of rasters written per step")
+    del rasters, enc
+    torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------- drop-in path
+
+def run_dropin(stack_np, L, want_blocks):
+    """The reference encoder's own call sequence (rti-builder/ptm-encoder.c:316-353,406) through the ptmlib.h
+    drop-in (libptm.so), pageable host memory in and out.  Returns the e2e_dropin object."""
+    from rti_b200 import ptmlib
+    n, H, W, _ = stack_np.shape
+    M = ptmlib.ptm_svd(L)
+
+    def once():
+        t0 = time.perf_counter()
+        res = ptmlib.encode_lrgb_stepwise(stack_np, M)
+        return time.perf_counter() - t0, res
+
+    once()
+    times = []
+    res = None
+    for _ in range(2):
+        dt, res = once()
+        times.append(dt)
+    s = min(times)
+    same = bool(np.array_equal(res["coef"].reshape(-1, 6), want_blocks[0]) and
+                np.array_equal(res["rgb"].reshape(-1, 3), want_blocks[1]))
+    return {"value": W * H / s / 1e6, "unit": "Mpixel/s", "ms_per_step": s * 1e3,
+            "h2d_bytes_per_step": int(stack_np.nbytes), "d2h_bytes_per_step": int(W * H * 9),
+            "calls": "ptm_fit_poly_jsample -> ptm_cbcr_avg -> ptm_lrgb_finish -> ptm_scale_coefficients (libptm.so)",
+            "host_memory": "pageable (numpy)", "identical_to_device_path": same}
 
 
 # ------------------------------------------------------------------- B200 arm
@@ -215,8 +446,8 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_cpus = bind_to_gpu_numa_node(physical_gpu_index(local)) if world > 1 else 0
     if world > 1:
-        bind_to_gpu_numa_node(physical_gpu_index(local))
         # NCCL announces its version on stdout at communicator creation when NCCL_DEBUG=VERSION is set in the
         # environment; stdout must carry the one JSON line only, so it points at stderr until NCCL is up
         sys.stdout.flush()
@@ -249,6 +480,12 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def allmax(values):
+        t = torch.tensor(values, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
 
     def step():
         enc.encode(stack)
@@ -288,15 +525,13 @@ def run_b200(args):
         k1_ms = float(np.mean(enc.ctx.probe_read(args.steps)))
     else:
         k1_ms = float(np.mean([a.elapsed_time(b) for a, b in k1_events]))
-    tt = torch.tensor([ms_total, k1_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total, k1_ms = tt.tolist()
+    ms_total, k1_ms = allmax([ms_total, k1_ms])
     ms_step = ms_total / args.steps
     value = W * H / (ms_step * 1e-3) / 1e6
 
     # ---- end to end through the host-buffer C-ABI call
     e2e = None
+    host_stack = None
     if not args.no_e2e:
         ctx = Context(local, stream=torch.cuda.current_stream().cuda_stream)
         host_stack = torch.empty((N_LIGHTS, rows, W, 3), dtype=torch.uint8).pin_memory()
@@ -304,6 +539,20 @@ def run_b200(args):
         out_coef = torch.empty((rows, W, 6), dtype=torch.uint8).pin_memory()
         out_rgb = torch.empty((rows, W, 3), dtype=torch.uint8).pin_memory()
         keys = torch.empty(12, dtype=torch.int32, device="cuda")
+
+        # the ceiling: the same pinned buffer copied to the device with nothing else going on, all ranks at once
+        scratch = torch.empty_like(stack)
+        scratch.copy_(host_stack, non_blocking=True)
+        barrier()
+        ca, cb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ca.record()
+        for _ in range(2):
+            scratch.copy_(host_stack, non_blocking=True)
+        cb_.record()
+        barrier()
+        (h2d_ms,) = allmax([ca.elapsed_time(cb_) / 2])
+        del scratch
+        h2d_peak_gbs = N_LIGHTS * W * H * 3 / (h2d_ms * 1e-3) / 1e9     # aggregate over all ranks
 
         def e2e_step():
             ctx.encode_host_fit(host_stack.data_ptr(), (N_LIGHTS, rows, W), U8, M, planes=1, keys_out=keys,
@@ -315,22 +564,30 @@ def run_b200(args):
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            res = e2e_step()                                  # synchronous: returns after the D2H
+            e2e_step()                                        # synchronous: returns after the D2H
         barrier()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e_s = dt.item() / args.e2e_steps
+        (e2e_s,) = allmax([time.perf_counter() - t0])
+        e2e_s /= args.e2e_steps
         # the host path must give the same bytes as the device-resident one
         assert torch.equal(out_coef.reshape(-1, 6), enc.coef_bytes[0].cpu()), "e2e bytes differ from device path"
         assert torch.equal(out_rgb.reshape(-1, 3), enc.rgb.cpu()), "e2e colour block differs from device path"
-        assert torch.equal(out_rgb.reshape(-1, 3), enc.rgb.cpu())
+        h2d_gbs = N_LIGHTS * W * H * 3 / e2e_s / 1e9
         e2e = {"value": W * H / e2e_s / 1e6, "unit": "Mpixel/s",
                "h2d_bytes_per_step": int(host_stack.numel()), "d2h_bytes_per_step": int(out_coef.numel() + out_rgb.numel()),
                "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
+               "h2d_gbs": h2d_gbs, "h2d_peak_gbs": h2d_peak_gbs, "frac_of_h2d_peak": h2d_gbs / h2d_peak_gbs,
+               "h2d_peak_note": "aggregate rate of plain pinned cudaMemcpyAsync of the same buffers, all ranks at once",
+               "numa_bound_cpus": numa_cpus,
+               "identical_to_device_path": True,
                "note": "per-rank bytes; pinned host stack -> ptmb_encode_host_fit/finish -> pinned host blocks"}
-        del host_stack
         ctx.close()
+
+    # ---- N > 1: the sharded blocks must equal a single-GPU encode of the whole image
+    sharded = None
+    if world > 1:
+        same, digest = sharded_identity(enc, M, L, W, H, r0, r1, world)
+        sharded = {"sharded_identical": same, "single_gpu_blocks_sha256": digest,
+                   "how": "every rank encodes the whole image on its own GPU (no exchange) and compares its slab"}
 
     if rank != 0:
         if world > 1:
@@ -338,39 +595,49 @@ def run_b200(args):
         return
 
     peak, peak_src = measured_peak()
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if world == 1 and os.path.exists(tpath) and (W, H) == (WIDTH, HEIGHT):
-        try:
-            traffic = float(json.load(open(tpath))["fit_lrgb_u8_tma_kernel"]["dram_bytes_per_launch"])
-        except Exception:
-            traffic = None
     k1_gbs = ALG_BYTES_K1 * P / (k1_ms * 1e-3) / 1e9
     path_gbs = ALG_BYTES_PATH * W * H / (ms_step * 1e-3) / 1e9 / world
+    traffic, traffic_src = (None, "single-GPU captures only")
+    if world == 1 and (W, H) == (WIDTH, HEIGHT):
+        per, traffic_src = read_traffic(["fit_lrgb_u8_tma_kernel", "quantise_kernel"])
+        traffic = None if per is None else sum(per.values())
     out = {
         "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "24MP (%dx%d) x %d lights dome1.lp, LRGB uint8, row-sharded over %d GPU(s)"
-                               % (W, H, N_LIGHTS, world),
+        "config": {"workload": WORKLOAD % (W * H / 1e6, W, H, N_LIGHTS), "sharding": "row slabs over %d GPU(s)" % world,
                    "rows_per_gpu": rows, "l2": "inputs larger than L2 (%.0f MB stack per GPU, streamed once per step)"
                                                % (stack.numel() / 1e6),
+                   "driver": "one process per GPU (torchrun)" if world > 1 else "one process",
                    "exchange": {"none": "none", "nccl": "int32 MAX all-reduce of 12 keys (NCCL)",
                                 "p2p": "12 int32 keys written into every peer's mailbox over NVLink by K1's last block, picked up in K2's prologue"}
                                [enc.exchange_kind]},
-        "roofline": {"bound": "hbm", "kernel": "fit_lrgb_u8 (K1)", "achieved": k1_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": k1_gbs / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_px": ALG_BYTES_K1, "k1_ms": k1_ms,
-                     "path_achieved": path_gbs, "path_frac": path_gbs / peak,
-                     "path_algorithmic_bytes_per_px": ALG_BYTES_PATH},
+        "roofline": {"bound": "hbm", "kernel": "fit path K1 + K2 (fit_lrgb_u8_tma_kernel dominant)",
+                     "achieved": path_gbs, "peak": peak, "unit": "GB/s", "frac": path_gbs / peak,
+                     "algorithmic_bytes_per_px": ALG_BYTES_PATH, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_ratio": None if traffic is None else traffic / (ALG_BYTES_PATH * W * H),
+                     "traffic_source": traffic_src,
+                     "k1_ms": k1_ms, "k1_achieved": k1_gbs, "k1_frac": k1_gbs / peak,
+                     "k1_algorithmic_bytes_per_px": ALG_BYTES_K1,
+                     "k1_share_of_step": k1_ms / ms_step},
         "clocks": clocks,
         "gpu_launches": args.steps * enc.launches_per_encode,
     }
     if e2e:
         out["e2e"] = e2e
-    if world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as O  # noqa: F401  (cpu_baseline leg: the one place bench may run the oracle)
-        out["cpu_baseline"] = cpu_baseline(W, L, M, args.cpu_seconds)
+    if sharded:
+        out["parity"] = sharded
+    if world == 1:
+        if not args.no_extra and (W, H) == (WIDTH, HEIGHT):
+            # release the headline stack first: configs[3] alone is 30 GB + 26 GB of rasters for configs[4]
+            out["extra"] = run_extras(M, L, peak, physical_gpu_index(local))
+        if not args.no_cpu_baseline:
+            from oracle import oracle as O  # noqa: F401  (cpu_baseline leg: the one place bench may run the oracle)
+            stack_np = host_stack.numpy() if host_stack is not None else stack.cpu().numpy()
+            out["cpu_baseline"], ref = cpu_baseline(stack_np, L, M, args.cpu_seconds)
+            out["parity"] = parity_vs_reference(enc, ref, M, stack_np)
+            if not args.no_dropin:
+                out["e2e_dropin"] = run_dropin(stack_np, L, (enc.coef_bytes[0].cpu().numpy(), enc.rgb.cpu().numpy()))
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -380,6 +647,9 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.driver == "c" and args.gpus > 1:
+        from rti_b200.multi import bench_multi          # single process, all GPUs through the C ABI
+        bench_multi(args, sys.modules[__name__])
     else:
         run_b200(args)
 

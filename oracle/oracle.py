@@ -70,6 +70,9 @@ def lib():
     L.orc_normal.restype = None
     L.orc_blas_corename.restype = C.c_char_p
     L.orc_blas_set_threads.argtypes = [C.c_int]
+    L.orc_omp_set_threads.argtypes = [C.c_int]
+    L.orc_omp_max_threads.restype = C.c_int
+    L.orc_omp_team_size.restype = C.c_int
     L.synth_light_q14.argtypes = [_f32p, C.c_int, _i32p]
     L.synth_stack_u8.argtypes = [C.c_uint32, C.c_int, C.c_uint32, C.c_size_t, C.c_uint32, _i32p, _u8p]
     L.synth_stack_u16.argtypes = [C.c_uint32, C.c_int, C.c_uint32, C.c_size_t, C.c_uint32, _i32p, _u16p]
@@ -78,6 +81,22 @@ def lib():
 
 
 # ------------------------------------------------------------------ helpers
+
+def host_cores():
+    """CPUs this process may run on."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def set_threads(n=None):
+    """OpenMP team size of the oracle AND of the reference's libptmref.so (one libgomp per process), set
+    through the library: launchers like torchrun export OMP_NUM_THREADS=1, and an environment variable
+    changed after libgomp is loaded is ignored.  Returns the team size a parallel region really gets."""
+    lib().orc_omp_set_threads(int(n or host_cores()))
+    return int(lib().orc_omp_team_size())
+
 
 def pinv(lights):
     """6 x n pseudo-inverse of the light matrix (LAPACKE path of the reference)."""
@@ -414,7 +433,7 @@ def cpu_encode_lrgb_timed(stack, M, use_ref=None, threads=None):
     if use_ref is None:
         use_ref = os.path.exists(os.path.join(REF_DIR, "libptmref.so"))
     if threads:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
+        set_threads(threads)
     n, H, W, _ = stack.shape
     P = H * W
     M = np.ascontiguousarray(M, dtype=np.float32)

@@ -13,7 +13,7 @@
  * (doc_src/draw_light_illustrations.m:1-59, see tests/golden/octave_kat.json)
  * and (2) byte-for-byte comparison against the reference's own ptmlib.c and
  * command-line mains, compiled unmodified into oracle/_ref/ by oracle/Makefile
- * and run in the build container (tests/test_oracle_vs_ref.py).
+ * and run in the build container (tests/test_oracle.py::test_oracle_vs_reference_live).
  *
  * Every function cites the reference lines it follows.  Build flags mirror the
  * reference's (rti-builder/Makefile:5-7: gcc -O -std=c11 -fopenmp, no -march,
@@ -414,4 +414,28 @@ const char *orc_blas_corename (void) {
 
 void orc_blas_set_threads (int n) {
     openblas_set_num_threads (n);
+}
+
+/* OpenMP team size for every later parallel region of this process (this library's and the reference's
+ * libptmref.so share one libgomp).  An OMP_NUM_THREADS written into the environment after libgomp has been
+ * loaded is never read; launchers such as torchrun export OMP_NUM_THREADS=1 before the process starts. */
+#include <omp.h>
+void orc_omp_set_threads (int n) {
+    omp_set_dynamic (0);
+    omp_set_num_threads (n > 0 ? n : 1);
+}
+
+int orc_omp_max_threads (void) {
+    return omp_get_max_threads ();
+}
+
+/* threads a parallel region really gets (the number a benchmark should report) */
+int orc_omp_team_size (void) {
+    int n = 1;
+    #pragma omp parallel
+    {
+        #pragma omp master
+        n = omp_get_num_threads ();
+    }
+    return n;
 }

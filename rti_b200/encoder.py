@@ -76,7 +76,8 @@ class PtmEncoder:
     mapped), or "nccl" (int32 MAX all-reduce through torch.distributed)."""
 
     def __init__(self, width, rows, M, planes=1, device=None, group=None, keep_coeffs=True, exchange="p2p",
-                 engine="default"):
+                 engine="default", single=False):
+        """single=True: this encoder works alone even inside an initialised process group (no exchange)."""
         assert torch.cuda.is_available(), "rti_b200 needs a CUDA device (no CPU fallback)"
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.width, self.rows, self.planes = int(width), int(rows), int(planes)
@@ -94,9 +95,9 @@ class PtmEncoder:
         self.keys = torch.empty(NKEYS, dtype=torch.int32, device=dev)
         self.sb = torch.empty(NKEYS, dtype=torch.int32, device=dev)  # 6 floats + 6 ints, raw
         self.keep_coeffs = bool(keep_coeffs)
-        self.xchg = make_key_exchange(self.ctx, group) if exchange == "p2p" else None
+        self.xchg = make_key_exchange(self.ctx, group) if exchange == "p2p" and not single else None
         import torch.distributed as dist
-        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        multi = not single and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.exchange_kind = "none" if not multi else ("p2p" if self.xchg is not None else "nccl")
         # fused LRGB encode: K1 + K2; otherwise keys-init, K1, K2 per plane
         self.launches_per_encode = 2 if (self.planes == 1 and self.exchange_kind in ("none", "p2p")) else 3
@@ -127,7 +128,7 @@ class PtmEncoder:
         self._use_current_stream()
         if self.xchg is not None:
             self.xchg.allreduce_max(self.keys)
-        else:
+        elif self.exchange_kind != "none":
             allreduce_keys(self.keys, self.group)
 
     def quantise(self):

@@ -181,3 +181,26 @@ def ptm_normal(coeffs):
     o = [C.c_float() for _ in range(3)]
     lib().ptm_normal(c.ctypes.data, C.byref(o[0]), C.byref(o[1]), C.byref(o[2]))
     return tuple(x.value for x in o)
+
+
+def encode_lrgb_stepwise(stack, M):
+    """The reference encoder's LRGB call sequence, step by step, on HOST (pageable) numpy buffers
+    (rti-builder/ptm-encoder.c:313-353,406):
+
+        ptm_fit_poly_jsample -> ptm_cbcr_avg -> colour + normalise loop (ptm_lrgb_finish) -> ptm_scale_coefficients
+
+    stack: uint8 [n][H][W][3] (YCbCr, stored row order).  Returns dict(coef, rgb, scale, bias, coeffs)."""
+    assert stack.dtype == np.uint8 and stack.ndim == 4 and stack.shape[3] == 3 and stack.flags.c_contiguous
+    n, H, W, _ = stack.shape
+    info = image_info(W, H, n)
+    header = ptm_alloc_header("PTM_FORMAT_LRGB", W, H)
+    blocks = ptm_alloc_blocks(header)
+    M = np.ascontiguousarray(M, dtype=np.float32)
+    coeffs = np.empty((info.pixels, PTM_COEFFICIENTS), np.float32)
+    L = lib()
+    L.ptm_fit_poly_jsample(C.byref(info), stack.ctypes.data, 3, M.ctypes.data, coeffs.ctypes.data)
+    L.ptm_cbcr_avg(C.byref(info), stack.ctypes.data, blocks[1].ctypes.data)
+    L.ptm_lrgb_finish(C.byref(info), blocks[1].ctypes.data, coeffs.ctypes.data)
+    L.ptm_scale_coefficients(C.byref(header), coeffs.ctypes.data, _block_ptrs(blocks))
+    return dict(coef=blocks[0].reshape(H, W, PTM_COEFFICIENTS), rgb=blocks[1].reshape(H, W, RGB_COEFFICIENTS),
+                scale=np.array(header.scale, np.float32), bias=np.array(header.bias, np.int32), coeffs=coeffs)
