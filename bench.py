@@ -269,7 +269,7 @@ def parity_vs_reference(enc, ref, M, stack_np):
     # float coefficients: |delta| relative to the coefficient's scale sum_n |M_kn| y_n * 256 / mean(y)
     rows = np.linspace(0, H - 1, 16).astype(int)
     got_f = enc.coeffs[0].reshape(H, W, 6)[torch.from_numpy(rows).cuda()].cpu().numpy()
-    y = stack_np[:, rows, :, 0].astype(np.float64)
+    y = stack_np[:, rows][..., 0].astype(np.float64)          # [n][16][W]
     bound = np.einsum("kn,nrw->rwk", np.abs(M).astype(np.float64), y) * (256.0 / np.maximum(np.floor(y.sum(0) / y.shape[0]), 1.0))[..., None]
     rel = float((np.abs(got_f.astype(np.float64) - ref["coeffs"][rows].astype(np.float64)) / np.maximum(bound, 1e-30)).max())
     out = {

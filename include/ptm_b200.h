@@ -64,6 +64,9 @@ void ptmb_destroy (ptmb_ctx_t *ctx);
 int ptmb_set_stream (ptmb_ctx_t *ctx, void *stream);
 int ptmb_synchronize (ptmb_ctx_t *ctx);
 int ptmb_sm_count (const ptmb_ctx_t *ctx);
+/* the context's cudaStream_t and device ordinal (so that a host can record its own events on the stream) */
+void *ptmb_stream (const ptmb_ctx_t *ctx);
+int ptmb_device (const ptmb_ctx_t *ctx);
 
 /* Device memory helpers for hosts that have no allocator of their own. */
 int ptmb_malloc (ptmb_ctx_t *ctx, size_t bytes, void **dev);
@@ -228,6 +231,39 @@ void ptmb_xchg_destroy (ptmb_xchg_t *xchg);
 int ptmb_encode_lrgb_dev (ptmb_ctx_t *ctx, ptmb_xchg_t *xchg, const void *stack_dev, int sample_type,
                           size_t image_stride, size_t pixels, float *coeffs_dev, uint8_t *rgb_dev,
                           uint8_t *coef_bytes_dev, ptmb_scale_bias_t *sb_dev);
+
+/* ---------------------------------------------------------------------------------------------
+ * One process, several GPUs.  The reference spreads ONE encode over the host's cores with an OpenMP
+ * loop over image rows (rti-builder/ptmlib.c:704,739,774,829,869); this is the same split over GPUs:
+ * GPU i of n owns the contiguous row slab [floor(i*H/n), floor((i+1)*H/n)), fits it, the 12 extrema
+ * keys are merged through in-process peer mailboxes over NVLink (cudaDeviceEnablePeerAccess -- no IPC
+ * handles, no collective library), and every GPU quantises its slab.  Results are byte-identical to
+ * the single-GPU call (integer max of order-preserving keys is exact).
+ *
+ *   ptmb_multi_create          devices = NULL / n_dev <= 0: all visible GPUs.  One context, one stream
+ *                              and one issuing host thread per GPU.
+ *   ptmb_multi_ctx             the context of GPU i (memory helpers, ptmb_synth, ptmb_stream, ...)
+ *   ptmb_multi_slab            the rows GPU i owns for an image of `height` rows
+ *   ptmb_multi_encode_host     ptmb_encode_host across the GPUs: ONE host stack / ONE set of host blocks
+ *                              in the caller's layout; each GPU streams its rows (synchronous)
+ *   ptmb_multi_encode_lrgb_dev ptmb_encode_lrgb_dev on every GPU's resident slab (arrays of n_dev
+ *                              entries); asynchronous, ptmb_multi_synchronize waits
+ * This is what ptm_encode_stack / the ptm-encoder command line use when PTM_B200_DEVICES=0,1,... is set. */
+typedef struct ptmb_multi ptmb_multi_t;
+int ptmb_multi_create (const int *devices, int n_dev, ptmb_multi_t **multi);
+void ptmb_multi_destroy (ptmb_multi_t *multi);
+int ptmb_multi_device_count (const ptmb_multi_t *multi);
+ptmb_ctx_t *ptmb_multi_ctx (ptmb_multi_t *multi, int i);
+int ptmb_multi_slab (const ptmb_multi_t *multi, size_t height, int i, size_t *row0, size_t *row1);
+int ptmb_multi_set_matrix (ptmb_multi_t *multi, const float *M, unsigned n_lights);
+int ptmb_multi_synchronize (ptmb_multi_t *multi);
+int ptmb_multi_encode_host (ptmb_multi_t *multi, const void *stack_host, int sample_type, size_t width,
+                            size_t height, unsigned n_lights, const float *M, int format_planes,
+                            uint8_t *const *blocks_host, float *coeffs_host, ptmb_scale_bias_t *sb_host);
+int ptmb_multi_encode_lrgb_dev (ptmb_multi_t *multi, const void *const *stack_dev, int sample_type,
+                                const size_t *image_stride, const size_t *pixels, float *const *coeffs_dev,
+                                uint8_t *const *rgb_dev, uint8_t *const *coef_bytes_dev,
+                                ptmb_scale_bias_t *const *sb_dev);
 
 /* Timing probes for benchmarks: the next `pairs` ptmb_encode_lrgb_dev calls bracket their fit
  * stage with CUDA events on the context's stream; _read synchronises and returns milliseconds. */

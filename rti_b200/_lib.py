@@ -34,6 +34,8 @@ _SIGNATURES = {
     "ptmb_set_stream": ([_vp, _vp], _int),
     "ptmb_synchronize": ([_vp], _int),
     "ptmb_sm_count": ([_vp], _int),
+    "ptmb_stream": ([_vp], _vp),
+    "ptmb_device": ([_vp], _int),
     "ptmb_malloc": ([_vp, _sz, C.POINTER(_vp)], _int),
     "ptmb_free": ([_vp, _vp], _int),
     "ptmb_upload": ([_vp, _vp, _vp, _sz], _int),
@@ -69,6 +71,15 @@ _SIGNATURES = {
     "ptmb_xchg_status": ([_vp, _vp, C.POINTER(C.c_int)], _int),
     "ptmb_xchg_destroy": ([_vp], None),
     "ptmb_encode_lrgb_dev": ([_vp, _vp, _vp, _int, _sz, _sz, _vp, _vp, _vp, _vp], _int),
+    "ptmb_multi_create": ([_vp, _int, C.POINTER(_vp)], _int),
+    "ptmb_multi_destroy": ([_vp], None),
+    "ptmb_multi_device_count": ([_vp], _int),
+    "ptmb_multi_ctx": ([_vp, _int], _vp),
+    "ptmb_multi_slab": ([_vp, _sz, _int, C.POINTER(_sz), C.POINTER(_sz)], _int),
+    "ptmb_multi_set_matrix": ([_vp, _vp, C.c_uint], _int),
+    "ptmb_multi_synchronize": ([_vp], _int),
+    "ptmb_multi_encode_host": ([_vp, _vp, _int, _sz, _sz, C.c_uint, _vp, _int, C.POINTER(_vp), _vp, _vp], _int),
+    "ptmb_multi_encode_lrgb_dev": ([_vp, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp], _int),
     "ptmb_probe_arm": ([_vp, C.c_uint], _int),
     "ptmb_probe_read": ([_vp, _vp, C.c_uint, C.POINTER(C.c_uint)], _int),
     "ptmb_jpeg_info": ([_vp, _vp, _sz, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)], _int),

@@ -48,6 +48,9 @@ const char *ptmb_last_error(void) { return g_error.c_str(); }
 int ptmb_internal_fail(const char *what, const char *detail) { return fail(what, detail); }
 int ptmb_internal_device(const ptmb_ctx_t *c) { return c->device; }
 void *ptmb_internal_stream(const ptmb_ctx_t *c) { return (void *) c->stream; }
+void *ptmb_stream(const ptmb_ctx_t *c) { return c ? (void *) c->stream : nullptr; }
+int ptmb_device(const ptmb_ctx_t *c) { return c ? c->device : -1; }
+int32_t *ptmb_internal_keys(ptmb_ctx_t *c) { return c->keys_dev; }
 const float *ptmb_internal_matrix(const ptmb_ctx_t *c) { return c->M_dev; }
 
 int ptmb_device_count(int *count) {
@@ -504,13 +507,6 @@ static int relight_common(ptmb_ctx_t *c, ptm::RelightArgs &a, bool lrgb, size_t 
         a.n_dirs = n_dirs - d0 < kBatch ? n_dirs - d0 : kBatch;
         a.light = c->light_dev + (size_t) d0 * PTMB_COEFFICIENTS;
         a.out = out_dev + (size_t) d0 * width * height * 3;
-        for (int k = 0; k < 5; ++k)
-            a.lmax[k] = 0.f;
-        for (unsigned d = d0; d < d0 + a.n_dirs; ++d)
-            for (int k = 0; k < 5; ++k) {
-                const float l = fabsf(c->light_host[(size_t) d * PTMB_COEFFICIENTS + k]);
-                a.lmax[k] = l > a.lmax[k] || l != l ? l : a.lmax[k];   // a NaN direction makes every pixel take the clamped loop
-            }
         cudaError_t e = fast ? ptm::launch_relight_fast(a, lrgb, c->sm_count, c->stream) : cudaErrorNotSupported;
         if (e == cudaErrorNotSupported)
             e = ptm::launch_relight(a, lrgb, c->sm_count, c->stream);
@@ -629,8 +625,11 @@ int ptmb_encode_host_early_rgb(ptmb_ctx_t *c, uint8_t *rgb_host) {
     return 0;
 }
 
-int ptmb_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, int sample_type, size_t width, size_t height,
-                         unsigned n_lights, const float *M, int format_planes, int32_t *keys_dev) {
+// `host_image_bytes`: distance between two lights' images in the HOST stack (>= one slab image; a row slab of
+// a larger image is passed with the pitch of the whole image -- the multi-GPU entry does that).
+int ptmb_internal_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, size_t host_image_bytes, int sample_type,
+                                  size_t width, size_t height, unsigned n_lights, const float *M, int format_planes,
+                                  int32_t *keys_dev) {
     REQUIRE(c && stack_host && M, "NULL argument");
     REQUIRE(format_planes == 1 || format_planes == 3, "format_planes must be 1 (LRGB) or 3 (RGB)");
     const size_t ss = sample_size(sample_type);
@@ -641,7 +640,8 @@ int ptmb_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, int sample_type,
         return 1;
     CK(cudaSetDevice(c->device));
 
-    const size_t image_bytes = pixels * 3 * ss;
+    const size_t image_bytes = host_image_bytes ? host_image_bytes : pixels * 3 * ss;
+    REQUIRE(image_bytes >= pixels * 3 * ss, "host image pitch smaller than one image");
     // slab: whole rows, about 8 MiB per light and slab
     size_t slab_rows = (8u << 20) / (width * 3 * ss);
     if (slab_rows < 1)
@@ -745,8 +745,15 @@ int ptmb_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, int sample_type,
     return 0;
 }
 
-int ptmb_encode_host_finish(ptmb_ctx_t *c, const int32_t *keys_dev, uint8_t *const *blocks_host,
-                            float *coeffs_host, ptmb_scale_bias_t *sb_host) {
+int ptmb_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, int sample_type, size_t width, size_t height,
+                         unsigned n_lights, const float *M, int format_planes, int32_t *keys_dev) {
+    return ptmb_internal_encode_host_fit(c, stack_host, 0, sample_type, width, height, n_lights, M, format_planes,
+                                         keys_dev);
+}
+
+// `coeffs_plane_floats`: distance between two coefficient planes in coeffs_host (0 = this slab's own size).
+int ptmb_internal_encode_host_finish(ptmb_ctx_t *c, const int32_t *keys_dev, uint8_t *const *blocks_host,
+                                     float *coeffs_host, size_t coeffs_plane_floats, ptmb_scale_bias_t *sb_host) {
     REQUIRE(c && blocks_host && sb_host, "NULL argument");
     EncodeScratch &s = c->enc;
     REQUIRE(s.valid, "ptmb_encode_host_fit has not been called");
@@ -768,13 +775,20 @@ int ptmb_encode_host_finish(ptmb_ctx_t *c, const int32_t *keys_dev, uint8_t *con
             CK(cudaMemcpyAsync(blocks_host[1], rgb_dev, pixels * 3, cudaMemcpyDeviceToHost, c->stream));
     }
     if (coeffs_host)
-        CK(cudaMemcpyAsync(coeffs_host, s.coeffs, plane_floats * s.planes * sizeof(float), cudaMemcpyDeviceToHost,
-                           c->stream));
+        for (int b = 0; b < s.planes; ++b)
+            CK(cudaMemcpyAsync(coeffs_host + (size_t) b * (coeffs_plane_floats ? coeffs_plane_floats : plane_floats),
+                               s.coeffs + (size_t) b * plane_floats, plane_floats * sizeof(float),
+                               cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(sb_host, c->sb_dev, sizeof(ptmb_scale_bias_t), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     s.valid = false;
     s.early_rgb_done = nullptr;
     return 0;
+}
+
+int ptmb_encode_host_finish(ptmb_ctx_t *c, const int32_t *keys_dev, uint8_t *const *blocks_host,
+                            float *coeffs_host, ptmb_scale_bias_t *sb_host) {
+    return ptmb_internal_encode_host_finish(c, keys_dev, blocks_host, coeffs_host, 0, sb_host);
 }
 
 int ptmb_encode_host(ptmb_ctx_t *c, const void *stack_host, int sample_type, size_t width, size_t height,

@@ -70,7 +70,6 @@ struct RelightArgs {
     const float *light;       // device [n_dirs][6]: u^2 v^2 uv u v 1
     unsigned n_dirs;
     uint8_t *out;             // [n_dirs][height][width][3]
-    float lmax[5];            // max over the batch of |u^2| |v^2| |uv| |u| |v| (range check of the tolerance kernels)
 };
 
 bool pack_mma_digits(const float *M, unsigned n_lights, std::vector<int8_t> &image, float *scale, unsigned *kpad_out);

@@ -6,24 +6,20 @@
 // the arithmetic:
 //
 //   * scale_k and the LRGB "/ 255.0f" (:595) are folded into the unscaled coefficients once per
-//     pixel, the polynomial (:58-63) is five fused multiply-adds on PIXEL PAIRS (fma.rn.f32x2);
-//   * CLIP (rti-builder/ptmlib.h:156-158: > 255 -> 255, < 0 -> 0, else truncate) is done on
-//     integers: the product L * colour is formed by fma.rz on top of 1.5 * 2^23, which leaves
-//     floor(x) as a two's-complement integer in the low mantissa bits; two values are moved into
-//     one register as s16x2 (PRMT) and clamped by ONE min.relu.s16x2; a last PRMT per four values
-//     gathers the bytes.  5 ALU instructions per 4 bytes instead of 11.
-//   * RGB formats (:610-619): the polynomial is accumulated ON TOP of 1.5 * 2^15, i.e. with 8
-//     fractional bits (<= 5 roundings of 2^-9: the sum is within 0.01 of the exact one), so bits
-//     8..23 of the accumulator already hold 0x4000 + floor(POLY): no separate truncation step.
+//     pixel; the polynomial (:58-63) is five fused multiply-adds on PIXEL PAIRS (fma.rn.f32x2).
+//   * CLIP (rti-builder/ptmlib.h:156-158: > 255 -> 255, < 0 -> 0, else truncate) without a single
+//     float compare or conversion: the value x is multiplied by 2^-149 with round-toward-zero
+//     (LRGB: the product L * colour itself, L pre-scaled by 2^-74 and the colour by 2^-75, both exact),
+//     which lands in the DENORMAL range, where the bit pattern of the float IS the integer: bits =
+//     floor(x) for x >= 0, sign bit + floor(|x|) for x < 0.  Read as s32 that is exactly what
+//     cvt.pack.sat.u8.s32 wants: one instruction saturates TWO values to 0..255 and packs them under
+//     two earlier bytes.  Per four output bytes: 2 packed multiplies + 2 I2IP, instead of
+//     4 min + 4 max + 4 truncating adds + 3 byte permutes.  No range restriction: negative -> 0,
+//     anything above 255 (up to +inf) -> 255.  Denormals are full speed in the FMA pipe.
 //
-// The 16-bit fields hold the value only while |x| < 2^15 (LRGB) / 2^14 (RGB).  A pixel whose
-// coefficients could exceed that for some direction of the batch (sum_k |a_k| * max_d |l_k(d)|,
-// evaluated once per pixel) takes the same loop with the polynomial clamped first; the clamp
-// cannot change a byte (clamped values are far outside 0..255 / their products are).
-//
-// Differences to the reference are confined to values within ~1e-3 (LRGB) / 1e-2 (RGB) of an
-// integer boundary: every byte is within 1 of the reference's (tests/test_gpu_relight_fast.py
-// counts them against the oracle).
+// Differences to the reference are confined to values within ~1e-4 of an integer boundary (fused
+// instead of separate roundings): every byte is within 1 of the reference's
+// (tests/test_gpu_relight_fast.py counts them against the oracle).
 #include <cstdlib>
 
 #include "ptm_device.cuh"
@@ -42,56 +38,33 @@ __device__ __forceinline__ f32x2 pk(float lo, float hi) {
     asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
     return d;
 }
-__device__ __forceinline__ void unpk_bits(f32x2 p, unsigned &lo, unsigned &hi) {
+__device__ __forceinline__ void unpk_bits(f32x2 p, int &lo, int &hi) {
     asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p));
-}
-__device__ __forceinline__ void unpk(f32x2 p, float &lo, float &hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p));
 }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     f32x2 d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
-__device__ __forceinline__ f32x2 fma2_rz(f32x2 a, f32x2 b, f32x2 c) {
+__device__ __forceinline__ f32x2 mul2_rz(f32x2 a, f32x2 b) {
     f32x2 d;
-    asm("fma.rz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    asm("mul.rz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-// max(min(a, b), 0) on two signed 16-bit lanes
-__device__ __forceinline__ unsigned min_relu_s16x2(unsigned a, unsigned b) {
+// (sat_u8(hi) << 8) | sat_u8(lo) in the low half, `upper`'s low half above it
+__device__ __forceinline__ unsigned pack_sat_u8(int hi, int lo, unsigned upper) {
     unsigned d;
-    asm("min.relu.s16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(upper));
     return d;
 }
-__device__ __forceinline__ unsigned min_u16x2(unsigned a, unsigned b) {
-    unsigned d;
-    asm("min.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
-__device__ __forceinline__ unsigned max_u16x2(unsigned a, unsigned b) {
-    unsigned d;
-    asm("max.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
+// four s32 values -> four saturated bytes, a in byte 0
+__device__ __forceinline__ unsigned bytes4(int a, int b, int c, int d) {
+    return pack_sat_u8(b, a, pack_sat_u8(d, c, 0u));
 }
 
-constexpr float kMagic23 = 12582912.0f;   // 1.5 * 2^23: ulp 1, low 16 mantissa bits = floor(x) mod 2^16
-constexpr float kMagic15 = 49152.0f;      // 1.5 * 2^15: ulp 2^-8, bits 8..23 = 0x4000 + floor(x)
-constexpr float kLrgbBound = 120.0f;      // |L| bound that keeps |L * colour| < 2^15
-constexpr float kRgbBound = 16000.0f;     // |POLY| bound that keeps 0x4000 + floor(x) inside 16 bits
-
-// four clamped bytes from four accumulators whose low 16 bits are signed integers
-__device__ __forceinline__ unsigned bytes_s16(unsigned a, unsigned b, unsigned c, unsigned d) {
-    const unsigned ab = min_relu_s16x2(__byte_perm(a, b, 0x5410), 0x00FF00FFu);
-    const unsigned cd = min_relu_s16x2(__byte_perm(c, d, 0x5410), 0x00FF00FFu);
-    return __byte_perm(ab, cd, 0x6420);
-}
-// the same from accumulators on top of 1.5 * 2^15: bits 8..23 = 0x4000 + floor(x)
-__device__ __forceinline__ unsigned bytes_q8(unsigned a, unsigned b, unsigned c, unsigned d) {
-    const unsigned ab = min_u16x2(max_u16x2(__byte_perm(a, b, 0x6521), 0x40004000u), 0x40FF40FFu);
-    const unsigned cd = min_u16x2(max_u16x2(__byte_perm(c, d, 0x6521), 0x40004000u), 0x40FF40FFu);
-    return __byte_perm(ab, cd, 0x6420);
-}
+constexpr float kTwoM74 = 5.29395592e-23f;    // 2^-74
+constexpr float kTwoM75 = 2.64697796e-23f;    // 2^-75
+constexpr float kTwoM149 = 1.40129846e-45f;   // 2^-149, the smallest denormal: x * 2^-149 (RZ) has bit pattern floor(x)
 
 // light table in shared memory: per direction six (l, l) pairs: u^2 v^2 uv u v, pad -- 48 bytes
 __device__ __forceinline__ void load_lights(float *light_s, const RelightArgs &a) {
@@ -118,43 +91,19 @@ __device__ __forceinline__ LightPairs light_pairs(const float *light_s, unsigned
 }
 
 // c5 + c0 l0 + ... + c4 l4 on a pixel pair, fused
-__device__ __forceinline__ f32x2 poly2(const f32x2 *c, const LightPairs &l, f32x2 c5) {
-    f32x2 s = fma2(c[4], l.l4, c5);
+__device__ __forceinline__ f32x2 poly2(const f32x2 *c, const LightPairs &l) {
+    f32x2 s = fma2(c[4], l.l4, c[5]);
     s = fma2(c[3], l.l3, s);
     s = fma2(c[2], l.l2, s);
     s = fma2(c[1], l.l1, s);
     return fma2(c[0], l.l0, s);
 }
 
-template <bool kClamp>
-__device__ __forceinline__ void lrgb_sweep(const RelightArgs &a, const float *light_s, const f32x2 (&A)[2][PTM_NCOEF],
-                                           const f32x2 (&C)[2][3], uint32_t *dst, size_t dir_words) {
-    const f32x2 kM = pk(kMagic23, kMagic23);
-#pragma unroll 2
-    for (unsigned d = 0; d < a.n_dirs; ++d) {
-        const LightPairs l = light_pairs(light_s, d);
-        unsigned z[2][3][2];   // [pair][channel][pixel of the pair]
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            f32x2 L = poly2(A[h], l, A[h][5]);
-            if (kClamp) {
-                float la, lb;
-                unpk(L, la, lb);
-                // NaN -> -bound: the reference's CLIP of a NaN product ends in byte 0 as well (x86 cvttss2si)
-                la = fminf(fmaxf(la, -kLrgbBound), kLrgbBound);
-                lb = fminf(fmaxf(lb, -kLrgbBound), kLrgbBound);
-                L = pk(la, lb);
-            }
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch)
-                unpk_bits(fma2_rz(L, C[h][ch], kM), z[h][ch][0], z[h][ch][1]);
-        }
-        // bytes p0r p0g p0b p1r | p1g p1b p2r p2g | p2b p3r p3g p3b
-        __stcs(dst + 0, bytes_s16(z[0][0][0], z[0][1][0], z[0][2][0], z[0][0][1]));
-        __stcs(dst + 1, bytes_s16(z[0][1][1], z[0][2][1], z[1][0][0], z[1][1][0]));
-        __stcs(dst + 2, bytes_s16(z[1][2][0], z[1][0][1], z[1][1][1], z[1][2][1]));
-        dst += dir_words;
-    }
+// bytes p0r p0g p0b p1r | p1g p1b p2r p2g | p2b p3r p3g p3b from z[pair][channel][pixel of the pair]
+__device__ __forceinline__ void store12(uint32_t *dst, const int (&z)[2][3][2]) {
+    __stcs(dst + 0, bytes4(z[0][0][0], z[0][1][0], z[0][2][0], z[0][0][1]));
+    __stcs(dst + 1, bytes4(z[0][1][1], z[0][2][1], z[1][0][0], z[1][1][0]));
+    __stcs(dst + 2, bytes4(z[1][2][0], z[1][0][1], z[1][1][1], z[1][2][1]));
 }
 
 // LRGB, 4 consecutive pixels of an output row per thread (width % 4 == 0).
@@ -169,7 +118,8 @@ relight_lrgb_fast_kernel(RelightArgs a) {
     float sc[PTM_NCOEF], kb[PTM_NCOEF];
 #pragma unroll
     for (int k = 0; k < PTM_NCOEF; ++k) {
-        sc[k] = a.scale[k] * 0.003921568627450980392f;   // scale_k / 255: L = POLY / 255 folded in
+        // scale_k / 255 (L = POLY / 255 folded in), times 2^-74 (exact): L' = L * 2^-74
+        sc[k] = (a.scale[k] * 0.003921568627450980392f) * kTwoM74;
         kb[k] = 8388608.0f + (float) a.bias[k];
     }
     for (size_t g = (size_t) blockIdx.x * blockDim.x + threadIdx.x; g < groups;
@@ -189,17 +139,7 @@ relight_lrgb_fast_kernel(RelightArgs a) {
         }
 #pragma unroll
         for (int j = 0; j < 12; ++j)
-            col[j / 3][j % 3] = byte_to_float(rw[j >> 2], 0x7650u + (j & 3));
-        // can |L| leave the range the 16-bit fields hold, for any direction of this batch?
-        bool safe = true;
-#pragma unroll
-        for (int px = 0; px < 4; ++px) {
-            float b = fabsf(u[px][5]);
-#pragma unroll
-            for (int k = 0; k < 5; ++k)
-                b = fmaf(fabsf(u[px][k]), a.lmax[k], b);
-            safe = safe && (b < kLrgbBound);   // false for NaN
-        }
+            col[j / 3][j % 3] = byte_to_float(rw[j >> 2], 0x7650u + (j & 3)) * kTwoM75;   // exact
         f32x2 A[2][PTM_NCOEF], C[2][3];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -212,46 +152,24 @@ relight_lrgb_fast_kernel(RelightArgs a) {
         }
         uint32_t *dst = reinterpret_cast<uint32_t *>(a.out + g * 12);
         const size_t dir_words = pixels * 3 / 4;
-        if (safe)
-            lrgb_sweep<false>(a, light_s, A, C, dst, dir_words);
-        else
-            lrgb_sweep<true>(a, light_s, A, C, dst, dir_words);
-    }
-}
-
-template <bool kClamp>
-__device__ __forceinline__ void rgb_sweep(const RelightArgs &a, const float *light_s,
-                                          const f32x2 (&A)[3][2][PTM_NCOEF], uint32_t *dst, size_t dir_words) {
 #pragma unroll 2
-    for (unsigned d = 0; d < a.n_dirs; ++d) {
-        const LightPairs l = light_pairs(light_s, d);
-        unsigned z[2][3][2];
+        for (unsigned d = 0; d < a.n_dirs; ++d) {
+            const LightPairs l = light_pairs(light_s, d);
+            int z[2][3][2];
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < 2; ++h) {
+                const f32x2 L = poly2(A[h], l);
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                if (kClamp) {
-                    // plain polynomial, clamp (NaN -> -bound -> byte 0, like the reference's CLIP on x86), then
-                    // onto the magic constant
-                    float sa, sb, ca, cb;
-                    unpk(poly2(A[ch][h], l, pk(0.f, 0.f)), sa, sb);
-                    unpk(A[ch][h][5], ca, cb);
-                    sa = fminf(fmaxf(sa + (ca - kMagic15), -kRgbBound), kRgbBound) + kMagic15;
-                    sb = fminf(fmaxf(sb + (cb - kMagic15), -kRgbBound), kRgbBound) + kMagic15;
-                    z[h][ch][0] = __float_as_uint(sa);
-                    z[h][ch][1] = __float_as_uint(sb);
-                } else {
-                    unpk_bits(poly2(A[ch][h], l, A[ch][h][5]), z[h][ch][0], z[h][ch][1]);
-                }
+                for (int ch = 0; ch < 3; ++ch)
+                    unpk_bits(mul2_rz(L, C[h][ch]), z[h][ch][0], z[h][ch][1]);   // (L 2^-74)(c 2^-75): bits = floor(L c)
             }
-        __stcs(dst + 0, bytes_q8(z[0][0][0], z[0][1][0], z[0][2][0], z[0][0][1]));
-        __stcs(dst + 1, bytes_q8(z[0][1][1], z[0][2][1], z[1][0][0], z[1][1][0]));
-        __stcs(dst + 2, bytes_q8(z[1][2][0], z[1][0][1], z[1][1][1], z[1][2][1]));
-        dst += dir_words;
+            store12(dst, z);
+            dst += dir_words;
+        }
     }
 }
 
-// RGB formats, 4 consecutive pixels per thread; constant terms carry 1.5 * 2^15.
+// RGB formats, 4 consecutive pixels per thread: CLIP(POLY) per channel (rti-builder/ptmlib.c:610-619).
 __global__ void __launch_bounds__(kThreads, 2)
 relight_rgb_fast_kernel(RelightArgs a) {
     extern __shared__ __align__(16) float light_s[];
@@ -260,6 +178,7 @@ relight_rgb_fast_kernel(RelightArgs a) {
     const size_t pixels = a.width * a.height;
     const size_t groups = pixels / 4;
     const size_t gw = a.width / 4;
+    const f32x2 kDen = pk(kTwoM149, kTwoM149);
     float kb[PTM_NCOEF];
 #pragma unroll
     for (int k = 0; k < PTM_NCOEF; ++k)
@@ -269,7 +188,6 @@ relight_rgb_fast_kernel(RelightArgs a) {
         const size_t y = g / gw, xg = g - y * gw;
         const size_t p = (a.height - 1 - y) * a.width + xg * 4;
         f32x2 A[3][2][PTM_NCOEF];
-        bool safe = true;
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
             const uint2 *c2 = reinterpret_cast<const uint2 *>(a.plane[ch] + p * PTM_NCOEF);
@@ -282,15 +200,6 @@ relight_rgb_fast_kernel(RelightArgs a) {
                 u[j / 6][j % 6] = a.scale[j % 6] * (m - kb[j % 6]);
             }
 #pragma unroll
-            for (int px = 0; px < 4; ++px) {
-                float b = fabsf(u[px][5]);
-#pragma unroll
-                for (int k = 0; k < 5; ++k)
-                    b = fmaf(fabsf(u[px][k]), a.lmax[k], b);
-                safe = safe && (b < kRgbBound);
-                u[px][5] += kMagic15;   // exact to 2^-8: the accumulator's own resolution
-            }
-#pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int k = 0; k < PTM_NCOEF; ++k)
@@ -298,10 +207,18 @@ relight_rgb_fast_kernel(RelightArgs a) {
         }
         uint32_t *dst = reinterpret_cast<uint32_t *>(a.out + g * 12);
         const size_t dir_words = pixels * 3 / 4;
-        if (safe)
-            rgb_sweep<false>(a, light_s, A, dst, dir_words);
-        else
-            rgb_sweep<true>(a, light_s, A, dst, dir_words);
+#pragma unroll 2
+        for (unsigned d = 0; d < a.n_dirs; ++d) {
+            const LightPairs l = light_pairs(light_s, d);
+            int z[2][3][2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+                    unpk_bits(mul2_rz(poly2(A[ch][h], l), kDen), z[h][ch][0], z[h][ch][1]);
+            store12(dst, z);
+            dst += dir_words;
+        }
     }
 }
 

@@ -74,6 +74,34 @@ static ptmb_ctx_t *gpu (void) {
     return g_ctx;
 }
 
+/* PTM_B200_DEVICES=0,1,...: ptm_encode_stack splits the image into one row slab per listed GPU (the reference
+ * spreads the same rows over host cores, ref :704).  NULL when the variable is not set or names one GPU. */
+static ptmb_multi_t *g_multi = NULL;
+
+static ptmb_multi_t *gpu_multi (void) {
+    static int tried = 0;
+    if (tried)
+        return g_multi;
+    tried = 1;
+    const char *list = getenv ("PTM_B200_DEVICES");
+    if (!list || !*list)
+        return NULL;
+    int devices[16], n = 0;
+    for (const char *p = list; *p && n < 16;) {
+        char *end = NULL;
+        const long d = strtol (p, &end, 10);
+        if (end == p)
+            break;
+        devices[n++] = (int) d;
+        p = *end == ',' ? end + 1 : end;
+    }
+    if (n < 2)
+        return NULL;
+    if (ptmb_multi_create (devices, n, &g_multi))
+        gpu_die ("ptmb_multi_create (PTM_B200_DEVICES)");
+    return g_multi;
+}
+
 /* for ptm_codec.c and the command lines (not part of ptmlib.h) */
 ptmb_ctx_t *ptm_internal_gpu (void) {
     return gpu ();
@@ -502,8 +530,13 @@ void ptm_encode_stack (ptm_header_t *h, const ptm_image_info_t *info, const JSAM
         free (coeffs);
         return;
     }
-    if (ptmb_encode_host (gpu (), buffer, PTMB_U8, info->width, info->height, info->n_decoders, M,
-                          h->format->ptm_blocks, blocks, NULL, &sb))
+    ptmb_multi_t *multi = gpu_multi ();
+    if (multi) {
+        if (ptmb_multi_encode_host (multi, buffer, PTMB_U8, info->width, info->height, info->n_decoders, M,
+                                    h->format->ptm_blocks, blocks, NULL, &sb))
+            gpu_die ("ptm_encode_stack (multi-GPU)");
+    } else if (ptmb_encode_host (gpu (), buffer, PTMB_U8, info->width, info->height, info->n_decoders, M,
+                                 h->format->ptm_blocks, blocks, NULL, &sb))
         gpu_die ("ptm_encode_stack");
     for (int i = 0; i < PTM_COEFFICIENTS; ++i) {
         h->scale[i] = sb.scale[i];

@@ -82,3 +82,124 @@ def test_two_gpu_slabs_equal_single_gpu():
         rgb = np.concatenate([ret[r][2][kind][4] for r in range(world)])
         np.testing.assert_array_equal(coef, full.coef_bytes[0].cpu().numpy())
         np.testing.assert_array_equal(rgb, full.rgb.cpu().numpy())
+
+
+# ---------------------------------------------------------------- one process, C ABI (ptmb_multi_*)
+
+def _single_gpu_reference(oracle_mod, W, H, planes, seed, mode):
+    from rti_b200 import lights
+    from rti_b200.device import Context
+    L = lights.dome1_lights()
+    M = oracle_mod.pinv(L)
+    stack = oracle_mod.synth_stack(seed, mode, W, H, L)
+    torch.cuda.set_device(0)
+    c = Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    want = c.encode_host(stack, M, planes=planes, want_coeffs=True)
+    c.close()
+    return L, M, stack, want
+
+
+@pytest.mark.parametrize("planes,mode", [(1, 0), (3, 1)])
+def test_multi_encode_host_equals_single_gpu(oracle, planes, mode):
+    """ptmb_multi_encode_host over every visible GPU (and over GPU 0 alone, the degenerate case that also runs on
+    a one-GPU box): blocks, float coefficients and scale / bias byte-identical to the single-GPU call.  Height
+    301 does not divide by the GPU count; width 128 gives slabs that are not tile multiples."""
+    from rti_b200.multi import MultiGpu
+    W, H = 128, 301
+    L, M, stack, want = _single_gpu_reference(oracle, W, H, planes, 0xD157, mode)
+    for devices in ([0], list(range(torch.cuda.device_count()))):
+        if len(devices) == 1 and devices != [0]:
+            continue
+        mg = MultiGpu(devices)
+        for _ in range(2):   # twice: mailbox epochs and scratch reuse
+            got = mg.encode_host(stack, M, planes=planes, want_coeffs=True)
+        for a, b in zip(got["blocks"], want["blocks"]):
+            np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(got["coeffs"], want["coeffs"])
+        np.testing.assert_array_equal(got["scale"], want["scale"])
+        np.testing.assert_array_equal(got["bias"], want["bias"])
+        print("ptmb_multi_encode_host on GPUs %s: identical to the single-GPU result" % devices)
+        mg.close()
+
+
+def test_multi_more_gpus_than_rows(oracle):
+    """Slabs may be empty (2 rows over up to 8 GPUs): empty GPUs still take part in the key exchange."""
+    from rti_b200.multi import MultiGpu
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    W, H = 64, 2
+    L, M, stack, want = _single_gpu_reference(oracle, W, H, 1, 0xD158, 0)
+    mg = MultiGpu(None)
+    got = mg.encode_host(stack, M, planes=1)
+    for a, b in zip(got["blocks"], want["blocks"]):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(got["bias"], want["bias"])
+    mg.close()
+
+
+def test_multi_encode_lrgb_dev_equals_single_gpu(oracle):
+    """Device-resident slabs through ptmb_multi_encode_lrgb_dev (K1 -> in-process NVLink mailboxes -> K2)."""
+    from rti_b200 import lights
+    from rti_b200.device import NCOEF
+    from rti_b200.encoder import PtmEncoder
+    from rti_b200.multi import MultiGpu
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    W, H = 1024, 96 * torch.cuda.device_count() + 5
+    L = lights.dome1_lights()
+    M = oracle.pinv(L)
+    stack = oracle.synth_stack(0xD159, 0, W, H, L)
+    torch.cuda.set_device(0)
+    full = PtmEncoder(W, H, M)
+    full.encode(torch.from_numpy(stack).cuda())
+    torch.cuda.synchronize()
+    mg = MultiGpu(None)
+    mg.set_matrix(M)
+    stacks, coeffs, rgbs, cbytes, sbs, slabs = [], [], [], [], [], []
+    for i in range(mg.n):
+        r0, r1 = mg.slab(H, i)
+        dev = torch.device("cuda", mg.devices[i])
+        P = (r1 - r0) * W
+        stacks.append(torch.from_numpy(np.ascontiguousarray(stack[:, r0:r1])).to(dev))
+        coeffs.append(torch.empty((P, NCOEF), dtype=torch.float32, device=dev))
+        rgbs.append(torch.empty((P, 3), dtype=torch.uint8, device=dev))
+        cbytes.append(torch.empty((P, NCOEF), dtype=torch.uint8, device=dev))
+        sbs.append(torch.empty(12, dtype=torch.int32, device=dev))
+        slabs.append((r0, r1))
+    for i in range(mg.n):
+        torch.cuda.synchronize(mg.devices[i])
+    a = mg.make_dev_args(stacks, coeffs, rgbs, cbytes, sbs)
+    for _ in range(5):
+        mg.encode_lrgb_dev(a)
+    mg.synchronize()
+    for i, (r0, r1) in enumerate(slabs):
+        assert torch.equal(cbytes[i].cpu(), full.coef_bytes[0][r0 * W:r1 * W].cpu())
+        assert torch.equal(rgbs[i].cpu(), full.rgb[r0 * W:r1 * W].cpu())
+        assert torch.equal(sbs[i].cpu(), full.sb.cpu())
+    mg.close()
+
+
+def test_ptm_encode_stack_uses_every_listed_gpu(oracle, tmp_path):
+    """The ptmlib.h drop-in with PTM_B200_DEVICES=0,1,...: ptm_encode_stack shards the rows; the PTM file written
+    by the command line is byte-identical to the single-GPU one."""
+    import subprocess
+    from conftest import ROOT
+    from rti_b200 import lights
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from test_gpu_cli import write_inputs
+    L = lights.dome1_lights()
+    W, H = 96, 50
+    stack = oracle.synth_stack(0xC12, 0, W, H, L)
+    lp = write_inputs(oracle, str(tmp_path), stack, L)
+    enc = os.path.join(ROOT, "rti_b200", "bin", "ptm-encoder")
+    outs = []
+    for devs in ("0", ",".join(str(i) for i in range(torch.cuda.device_count()))):
+        out = os.path.join(str(tmp_path), "out_%d.ptm" % len(outs))
+        env = dict(os.environ, PTM_IMAGE_CODEC="raw", OPENBLAS_NUM_THREADS="1")
+        env.pop("CUDA_VISIBLE_DEVICES", None)
+        env["PTM_B200_DEVICES" if "," in devs else "PTM_B200_DEVICE"] = devs
+        r = subprocess.run([enc, "-f", "PTM_FORMAT_LRGB", "-o", out, lp], capture_output=True, env=env)
+        assert r.returncode == 0, r.stderr.decode()
+        outs.append(open(out, "rb").read())
+    assert outs[0] == outs[1]

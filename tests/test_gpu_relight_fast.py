@@ -70,8 +70,7 @@ def test_rgb_sweep_within_one(ctx, oracle, dome1, M60):
 @pytest.mark.parametrize("fmt", ["lrgb", "rgb"])
 def test_random_blocks_and_out_of_range_pixels(ctx, oracle, fmt):
     """Uniformly random blocks with scales / biases that push the polynomial far outside 0..255 in both
-    directions (every pixel group then takes the clamped loop), next to tame ones (the plain loop): CLIP must
-    saturate exactly like the reference's, never wrap."""
+    directions (up to ~1e7), next to tame ones: CLIP must saturate exactly like the reference's, never wrap."""
     rng = np.random.default_rng(77)
     W, H = 48, 20
     uv = np.concatenate([ring(16, 0.9), [[0, 0], [3.0, -2.5]]]).astype(np.float32)
