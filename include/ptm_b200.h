@@ -114,6 +114,17 @@ int ptmb_keys_init (ptmb_ctx_t *ctx, int32_t *keys_dev);
 int ptmb_fit_lrgb (ptmb_ctx_t *ctx, const void *stack_dev, int sample_type, size_t image_stride,
                    size_t pixels, float *coeffs_dev, uint8_t *rgb_dev, int32_t *keys_dev);
 
+/* Variants of the LRGB-shaped entries (ptmb_fit_lrgb, ptmb_encode_lrgb_dev, ptmb_encode_host* with
+ * format_planes = 1); flags, 0 = plain PTM_FORMAT_LRGB.  uint8 stacks only.
+ *   PTMB_FIT_LUM        PTM_FORMAT_LUM (rti-builder/ptm-encoder.c:286-305): fit on Y, the colour block is the
+ *                       averaged YCbCr triplet as ptm_cbcr_avg leaves it, no colour conversion, no normalisation
+ *   PTMB_FIT_RGB_INPUT  the stack holds RGB triplets (not the YCbCr the reference's decoder delivers,
+ *                       rti-builder/ptm-encoder.c:188): every sample is converted to YCbCr first with libjpeg's
+ *                       integer JFIF formula, fused into K1 */
+#define PTMB_FIT_LUM       1
+#define PTMB_FIT_RGB_INPUT 2
+int ptmb_set_fit_mode (ptmb_ctx_t *ctx, int flags);
+
 /* K1, RGB formats: three fits (rti-builder/ptm-encoder.c:272-284) in one pass.
  * coeffs_dev: float [3][pixels][6] with `plane_stride` floats between planes.  Only plane 0
  * feeds the extrema, as in the reference (rti-builder/ptmlib.c:831). */
@@ -170,6 +181,31 @@ int ptmb_relight_lrgb (ptmb_ctx_t *ctx, const uint8_t *coef_dev, const uint8_t *
 int ptmb_relight_rgb (ptmb_ctx_t *ctx, const uint8_t *r_dev, const uint8_t *g_dev, const uint8_t *b_dev,
                       size_t width, size_t height, const float *scale, const int32_t *bias,
                       const float *uv, unsigned n_dirs, uint8_t *out_dev);
+
+/* PTM_FORMAT_LUM relighting (rti-builder/ptmlib.c:601-609): out triplets are (CLIP(POLY), Cb, Cr) -- a YCbCr
+ * raster -- with (Cr, Cb) read from crcb_dev as 2-byte records at the pixel's index, which is how the
+ * reference's loop addresses block 1.  Always the exact arithmetic. */
+int ptmb_relight_lum (ptmb_ctx_t *ctx, const uint8_t *coef_dev, const uint8_t *crcb_dev, size_t width,
+                      size_t height, const float *scale, const int32_t *bias, const float *uv, unsigned n_dirs,
+                      uint8_t *out_dev);
+
+/* Surface normals, ptm_normal (rti-builder/ptmlib.c:808-814, [Malzbender2001] eq. 16-17) for every pixel:
+ * normals_dev float [pixels][3] = (nu, nv, nw), the reference's expressions including the sign it has inside
+ * the square root.  From a float coefficient plane [pixels][6], or from a quantised block unscaled with the
+ * header's scale / bias (rti-builder/ptmlib.c:54). */
+int ptmb_normal_map (ptmb_ctx_t *ctx, const float *coeffs_dev, size_t pixels, float *normals_dev);
+int ptmb_normal_map_blocks (ptmb_ctx_t *ctx, const uint8_t *coef_dev, const float *scale, const int32_t *bias,
+                            size_t pixels, float *normals_dev);
+
+/* The reference encoder's disabled LRGB variant (rti-builder/ptm-encoder.c:356-400): luminance L = R + G + B of
+ * an RGB uint8 stack fitted like ptm_fit_poly_uint (coefficients NOT normalised), colour block
+ * (JSAMPLE) (256 * chroma_c / L_0) with L_0 the first light's sum, chroma_c = truncated mean over the lights
+ * (what the reference computes, PTMB_CHROMA_MEAN) or the median its FIXME asks for (:383, PTMB_CHROMA_MEDIAN:
+ * (lower + upper middle) / 2).  L_0 == 0 (a division by zero in the reference) stores 0. */
+#define PTMB_CHROMA_MEAN   0
+#define PTMB_CHROMA_MEDIAN 1
+int ptmb_fit_lsum (ptmb_ctx_t *ctx, const uint8_t *stack_dev, size_t image_stride, size_t pixels, int chroma,
+                   float *coeffs_dev, uint8_t *colour_dev, int32_t *keys_dev);
 
 /* Self test of K3's arithmetic shortcuts: compares the 3-instruction x / 255.0f and the CLIP
  * replacement with the IEEE division / the reference's CLIP (rti-builder/ptmlib.h:156-158) for
@@ -256,6 +292,7 @@ int ptmb_multi_device_count (const ptmb_multi_t *multi);
 ptmb_ctx_t *ptmb_multi_ctx (ptmb_multi_t *multi, int i);
 int ptmb_multi_slab (const ptmb_multi_t *multi, size_t height, int i, size_t *row0, size_t *row1);
 int ptmb_multi_set_matrix (ptmb_multi_t *multi, const float *M, unsigned n_lights);
+int ptmb_multi_set_fit_mode (ptmb_multi_t *multi, int flags);
 int ptmb_multi_synchronize (ptmb_multi_t *multi);
 int ptmb_multi_encode_host (ptmb_multi_t *multi, const void *stack_host, int sample_type, size_t width,
                             size_t height, unsigned n_lights, const float *M, int format_planes,
@@ -307,7 +344,11 @@ int ptmb_scale_host (ptmb_ctx_t *ctx, const float *coeffs_host, size_t pixels, i
                      uint8_t *const *blocks_host, ptmb_scale_bias_t *sb_host);
 int ptmb_relight_host (ptmb_ctx_t *ctx, const uint8_t *const *blocks_host, int planes, size_t width, size_t height,
                        const float *scale, const int32_t *bias, const float *uv, unsigned n_dirs,
-                       uint8_t *out_host);
+                       uint8_t *out_host);   /* planes: 1 = LRGB, 3 = RGB formats, 2 = LUM (blocks[1] = (cr, cb) records) */
+/* ptm_normal (rti-builder/ptmlib.c:808-814) for every pixel: exactly one of coeffs_host (float [pixels][6])
+ * and coef_bytes_host (uint8 [pixels][6] + scale / bias) is given; normals_host float [pixels][3]. */
+int ptmb_normal_map_host (ptmb_ctx_t *ctx, const float *coeffs_host, const uint8_t *coef_bytes_host,
+                          const float *scale, const int32_t *bias, size_t pixels, float *normals_host);
 
 #ifdef __cplusplus
 }

@@ -220,6 +220,10 @@ void ptm_relight (const ptm_header_t *ptm_header, ptm_block_t *blocks, float u, 
 void ptm_relight_batch (const ptm_header_t *ptm_header, ptm_block_t *blocks, const float *uv,
                         unsigned int n_dirs, JSAMPLE *out);
 
+/* ptm_normal for every pixel of a PTM (first coefficient block, unscaled with the header's scale / bias):
+ * normals float [height * width][3] = (nu, nv, nw) per stored pixel. */
+void ptm_normal_map (const ptm_header_t *ptm_header, ptm_block_t *blocks, float *normals);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,14 @@ def lib():
     L.orc_lrgb16_finish.restype = None
     L.orc_normal.argtypes = [_f32p, _f32p, _f32p, _f32p]
     L.orc_normal.restype = None
+    L.orc_normal_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, _f32p]
+    L.orc_normal_map.restype = None
+    L.orc_relight_lum.argtypes = [_u8p, _u8p, C.c_size_t, C.c_size_t, _f32p, _i32p, C.c_float, C.c_float, _u8p]
+    L.orc_relight_lum.restype = None
+    L.orc_rgb_to_ycbcr.argtypes = [_u8p, C.c_size_t]
+    L.orc_rgb_to_ycbcr.restype = None
+    L.orc_fit_lsum.argtypes = [_u8p, C.c_size_t, C.c_uint, _f32p, C.c_int, _f32p, _u8p]
+    L.orc_fit_lsum.restype = None
     L.orc_blas_corename.restype = C.c_char_p
     L.orc_blas_set_threads.argtypes = [C.c_int]
     L.orc_omp_set_threads.argtypes = [C.c_int]
@@ -258,6 +266,62 @@ def relight_rgb(coef3, scale_vals, bias, u, v):
                           np.ascontiguousarray(scale_vals, dtype=np.float32),
                           np.ascontiguousarray(bias, dtype=np.int32), u, v, out.reshape(-1))
     return out
+
+
+def normal_map(coeffs=None, coef_bytes=None, scale_vals=None, bias=None):
+    """ptm_normal for every pixel -> float32 [P][3]; from float coefficients [P][6] or from a quantised block."""
+    if coeffs is not None:
+        c = np.ascontiguousarray(coeffs, dtype=np.float32).reshape(-1, NCOEF)
+        out = np.zeros((c.shape[0], 3), np.float32)
+        lib().orc_normal_map(c.ctypes.data, None, None, None, c.shape[0], out.reshape(-1))
+        return out
+    b = np.ascontiguousarray(coef_bytes, dtype=np.uint8).reshape(-1, NCOEF)
+    sc = np.ascontiguousarray(scale_vals, dtype=np.float32)
+    bi = np.ascontiguousarray(bias, dtype=np.int32)
+    out = np.zeros((b.shape[0], 3), np.float32)
+    lib().orc_normal_map(None, b.ctypes.data, sc.ctypes.data, bi.ctypes.data, b.shape[0], out.reshape(-1))
+    return out
+
+
+def relight_lum(coef, crcb, scale_vals, bias, u, v):
+    """PTM_FORMAT_LUM relight (rti-builder/ptmlib.c:601-609): crcb = flat uint8 buffer read as 2-byte (cr, cb)
+    records (at least 2 bytes per pixel).  Returns the (Y, Cb, Cr) raster."""
+    H, W, _ = coef.shape
+    out = np.zeros((H, W, 3), dtype=np.uint8)
+    lib().orc_relight_lum(np.ascontiguousarray(coef).reshape(-1), np.ascontiguousarray(crcb).reshape(-1), W, H,
+                          np.ascontiguousarray(scale_vals, dtype=np.float32),
+                          np.ascontiguousarray(bias, dtype=np.int32), u, v, out.reshape(-1))
+    return out
+
+
+def rgb_to_ycbcr(stack):
+    """Per-sample integer JFIF conversion of an RGB stack (copy)."""
+    out = np.ascontiguousarray(stack, dtype=np.uint8).copy()
+    lib().orc_rgb_to_ycbcr(out.reshape(-1), out.size // 3)
+    return out
+
+
+def encode_lum(stack, M):
+    """PTM_FORMAT_LUM sequence (rti-builder/ptm-encoder.c:286-305,406): fit Y, average the triplets, scale --
+    no colour conversion, no normalisation.  Returns dict(coeffs, coef, ycc, scale, bias)."""
+    n, H, W, _ = stack.shape
+    coeffs = fit_u8(stack, M, 0)
+    ycc = chroma_avg(stack)
+    blocks, sc, bi, mm = scale(coeffs.reshape(-1, NCOEF), 1)
+    return dict(coeffs=coeffs, coef=blocks[0].reshape(H, W, NCOEF), ycc=ycc, scale=sc, bias=bi, minmax=mm)
+
+
+def fit_lsum(stack, M, median=False):
+    """The reference encoder's disabled L = R + G + B branch (rti-builder/ptm-encoder.c:356-400) + scale.
+    Returns dict(coeffs, coef, colour, scale, bias)."""
+    n, H, W, _ = stack.shape
+    M = np.ascontiguousarray(M, dtype=np.float32)
+    coeffs = np.zeros((H, W, NCOEF), np.float32)
+    colour = np.zeros((H, W, 3), np.uint8)
+    lib().orc_fit_lsum(np.ascontiguousarray(stack).reshape(-1), H * W, n, M.reshape(-1), 1 if median else 0,
+                       coeffs.reshape(-1), colour.reshape(-1))
+    blocks, sc, bi, mm = scale(coeffs.reshape(-1, NCOEF), 1)
+    return dict(coeffs=coeffs, coef=blocks[0].reshape(H, W, NCOEF), colour=colour, scale=sc, bias=bi, minmax=mm)
 
 
 def normal(c):

@@ -408,6 +408,92 @@ void orc_normal (const float *c, float *nu, float *nv, float *nw) {
     *nw = sqrtf (1.0f - *nu * *nu + *nv * *nv);
 }
 
+/* ptm_normal over a whole plane: from float coefficients [pixels][6], or (coeffs == NULL) from a quantised
+ * block unscaled with UNSCALE (rti-builder/ptmlib.c:54: scale * (byte - bias), int subtraction). */
+void orc_normal_map (const float *coeffs, const uint8_t *bytes, const float *scale, const int *bias,
+                     size_t pixels, float *normals) {
+    #pragma omp parallel for schedule(static)
+    for (size_t p = 0; p < pixels; ++p) {
+        float c[NCOEF];
+        for (int k = 0; k < NCOEF; ++k)
+            c[k] = coeffs ? coeffs[p * NCOEF + k] : scale[k] * (bytes[p * NCOEF + k] - bias[k]);
+        orc_normal (c, normals + p * 3, normals + p * 3 + 1, normals + p * 3 + 2);
+    }
+}
+
+/* rti-builder/ptmlib.c:601-609 -- the PTM_FORMAT_LUM branch of the relight loop.  Block 1 is addressed as
+ * crcb_coefficients_t (rti-builder/ptmlib.h: JSAMPLE cr, cb -- 2 bytes) at pixel index yoffs + x, exactly
+ * like the reference's pointer arithmetic; the raster holds (Y, Cb, Cr) triplets (JCS_YCbCr, :575). */
+void orc_relight_lum (const uint8_t *coef, const uint8_t *crcb, size_t width, size_t height,
+                      const float *scale, const int *bias, float u, float v, uint8_t *out) {
+    const float light[NCOEF] = { u * u, v * v, u * v, u, v, 1.0f };
+    #pragma omp parallel for schedule(static)
+    for (size_t y = 0; y < height; ++y) {
+        const size_t src = (height - 1 - y) * width;
+        uint8_t *o = out + y * width * 3;
+        for (size_t x = 0; x < width; ++x, o += 3) {
+            o[0] = clip_u8 (orc_poly (coef + (src + x) * NCOEF, scale, bias, light));
+            o[1] = clip_u8 (crcb[(src + x) * 2 + 1]);   /* cb */
+            o[2] = clip_u8 (crcb[(src + x) * 2]);       /* cr */
+        }
+    }
+}
+
+/* RGB -> YCbCr per sample, in place: libjpeg's integer JFIF conversion (jccolor.c rgb_ycc_convert;
+ * third party, absent from /root/reference: FIX(x) = (int) (x * 65536 + 0.5), ONE_HALF = 32768,
+ * CBCR_OFFSET = 128 << 16).  The reference never runs it (its decoder delivers YCbCr,
+ * rti-builder/ptm-encoder.c:188): this is the host statement of the optional RGB-input front end
+ *  -- PARITY UNPINNED for this function: neither the reference nor this image
+ * exposes libjpeg's converter on its own; tests/test_oracle.py checks it against the real-valued JFIF
+ * matrix (within 1) and against known triplets. */
+void orc_rgb_to_ycbcr (uint8_t *samples, size_t n_triplets) {
+    #pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n_triplets; ++i) {
+        uint8_t *t = samples + i * 3;
+        const unsigned r = t[0], g = t[1], b = t[2];
+        t[0] = (uint8_t) ((19595u * r + 38470u * g + 7471u * b + 32768u) >> 16);
+        t[1] = (uint8_t) ((8388608u + 32767u + 32768u * b - 11059u * r - 21709u * g) >> 16);
+        t[2] = (uint8_t) ((8388608u + 32767u + 32768u * r - 27439u * g - 5329u * b) >> 16);
+    }
+}
+
+static int cmp_u8 (const void *a, const void *b) {
+    return (int) *(const uint8_t *) a - (int) *(const uint8_t *) b;
+}
+
+/* rti-builder/ptm-encoder.c:356-400 -- the disabled LRGB branch (color_components == 666).
+ *   :366-372  L = R + G + B for every sample
+ *   :376-380  ptm_fit_poly_uint on L (pixel stride 1): unnormalised coefficients
+ *   :384-386  ptm_cbcr_avg over the RGB triplets (truncated mean) -- "FIXME should use median here!" (:383);
+ *             median != 0 computes that median instead ((lower + upper middle) / 2; EXTENSION, the
+ *             reference has no arithmetic for it)
+ *   :391-399  colour = 256 * (int) mean / *l, stored into a JSAMPLE, with l walking L[0 .. pixels): the sums
+ *             of the FIRST light.  *l == 0 is a division by zero there; 0 is stored here.
+ * stack: uint8 [n][pixels][3] RGB. */
+void orc_fit_lsum (const uint8_t *stack, size_t pixels, unsigned n_lights, const float *M, int median,
+                   float *coeffs, uint8_t *colour) {
+    unsigned int *L = malloc (sizeof (unsigned int) * (size_t) n_lights * pixels);
+    for (size_t i = 0; i < (size_t) n_lights * pixels; ++i)
+        L[i] = (unsigned int) stack[i * 3] + stack[i * 3 + 1] + stack[i * 3 + 2];
+    orc_fit_u32 (L, pixels, 1, n_lights, 1, M, coeffs);
+    orc_chroma_avg (stack, pixels, n_lights, colour);
+    #pragma omp parallel for schedule(static)
+    for (size_t p = 0; p < pixels; ++p) {
+        for (int ch = 0; ch < 3; ++ch) {
+            unsigned int c = colour[p * 3 + ch];
+            if (median) {
+                uint8_t v[2048];
+                for (unsigned n = 0; n < n_lights; ++n)
+                    v[n] = stack[((size_t) n * pixels + p) * 3 + ch];
+                qsort (v, n_lights, 1, cmp_u8);
+                c = ((unsigned int) v[(n_lights - 1) / 2] + v[n_lights / 2]) / 2;
+            }
+            colour[p * 3 + ch] = L[p] ? (uint8_t) (256 * (int) c / L[p]) : 0;
+        }
+    }
+    free (L);
+}
+
 const char *orc_blas_corename (void) {
     return openblas_get_corename ();
 }

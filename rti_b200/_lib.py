@@ -14,6 +14,7 @@ NCOEF = 6
 NKEYS = 12
 U8, U16, U32 = 0, 1, 2
 SYNTH_YCBCR, SYNTH_RGB = 0, 1
+FIT_LUM, FIT_RGB_INPUT = 1, 2
 
 
 class PtmError(RuntimeError):
@@ -48,6 +49,7 @@ _SIGNATURES = {
     "ptmb_mma_pack_digits": ([_vp, C.c_uint, _vp, _sz, _vp, _vp], _int),
     "ptmb_keys_init": ([_vp, _vp], _int),
     "ptmb_fit_lrgb": ([_vp, _vp, _int, _sz, _sz, _vp, _vp, _vp], _int),
+    "ptmb_set_fit_mode": ([_vp, _int], _int),
     "ptmb_fit_rgb": ([_vp, _vp, _int, _sz, _sz, _vp, _sz, _vp], _int),
     "ptmb_fit_channel": ([_vp, _vp, _int, _sz, _sz, _sz, _vp], _int),
     "ptmb_chroma_avg": ([_vp, _vp, _sz, _sz, C.c_uint, _vp], _int),
@@ -58,6 +60,10 @@ _SIGNATURES = {
     "ptmb_set_relight_mode": ([_vp, _int], _int),
     "ptmb_relight_lrgb": ([_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, C.c_uint, _vp], _int),
     "ptmb_relight_rgb": ([_vp, _vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, C.c_uint, _vp], _int),
+    "ptmb_relight_lum": ([_vp, _vp, _vp, _sz, _sz, _vp, _vp, _vp, C.c_uint, _vp], _int),
+    "ptmb_normal_map": ([_vp, _vp, _sz, _vp], _int),
+    "ptmb_normal_map_blocks": ([_vp, _vp, _vp, _vp, _sz, _vp], _int),
+    "ptmb_fit_lsum": ([_vp, _vp, _sz, _sz, _int, _vp, _vp, _vp], _int),
     "ptmb_selftest_div255": ([_vp, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)], _int),
     "ptmb_synth": ([_vp, _u32, _int, _int, _u32, _sz, C.c_uint, _vp, _vp, _sz], _int),
     "ptmb_encode_host_early_rgb": ([_vp, _vp], _int),
@@ -77,6 +83,7 @@ _SIGNATURES = {
     "ptmb_multi_ctx": ([_vp, _int], _vp),
     "ptmb_multi_slab": ([_vp, _sz, _int, C.POINTER(_sz), C.POINTER(_sz)], _int),
     "ptmb_multi_set_matrix": ([_vp, _vp, C.c_uint], _int),
+    "ptmb_multi_set_fit_mode": ([_vp, _int], _int),
     "ptmb_multi_synchronize": ([_vp], _int),
     "ptmb_multi_encode_host": ([_vp, _vp, _int, _sz, _sz, C.c_uint, _vp, _int, C.POINTER(_vp), _vp, _vp], _int),
     "ptmb_multi_encode_lrgb_dev": ([_vp, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp], _int),
@@ -89,6 +96,7 @@ _SIGNATURES = {
     "ptmb_chroma_avg_host": ([_vp, _vp, _sz, C.c_uint, _vp], _int),
     "ptmb_lrgb_colour_normalise_host": ([_vp, _vp, _vp, _sz], _int),
     "ptmb_scale_host": ([_vp, _vp, _sz, _int, C.POINTER(_vp), _vp], _int),
+    "ptmb_normal_map_host": ([_vp, _vp, _vp, _vp, _vp, _sz, _vp], _int),
     "ptmb_relight_host": ([_vp, C.POINTER(_vp), _int, _sz, _sz, _vp, _vp, _vp, C.c_uint, _vp], _int),
 }
 

@@ -258,6 +258,7 @@ static int make_fit_args(ptmb_ctx_t *c, const void *stack_dev, size_t image_stri
     memcpy(a.digit_scale, c->digit_scale, sizeof(a.digit_scale));
     a.kpad = c->kpad;
     a.engine = c->engine;
+    a.mode = 0;   // the LRGB-shaped entries set it from the context (ptmb_set_fit_mode)
     a.tile_counter = c->ticket_dev ? c->ticket_dev + 1 : nullptr;
     static int store_hint = -1;
     if (store_hint < 0) {
@@ -280,8 +281,17 @@ int ptmb_fit_lrgb(ptmb_ctx_t *c, const void *stack_dev, int sample_type, size_t 
     a.coeffs = coeffs_dev;
     a.rgb = rgb_dev;
     a.keys = keys_dev;
+    a.mode = c->fit_mode;
+    REQUIRE(a.mode == 0 || sample_type == PTMB_U8, "PTM_FORMAT_LUM / RGB-input stacks are 8-bit paths");
     CK(cudaSetDevice(c->device));
     CK(ptm::launch_fit_lrgb(a, sample_type, c->sm_count, c->stream));
+    return 0;
+}
+
+int ptmb_set_fit_mode(ptmb_ctx_t *c, int flags) {
+    REQUIRE(c, "ctx is NULL");
+    REQUIRE((flags & ~(PTMB_FIT_LUM | PTMB_FIT_RGB_INPUT)) == 0, "unknown fit mode flag");
+    c->fit_mode = flags;
     return 0;
 }
 
@@ -375,6 +385,8 @@ int ptmb_encode_lrgb_dev(ptmb_ctx_t *c, ptmb_xchg_t *x, const void *stack_dev, i
     a.coeffs = coeffs_dev;
     a.rgb = rgb_dev;
     a.keys = c->keys_dev;   // kept at the initial extrema between encodes (reset by the hand-off)
+    a.mode = c->fit_mode;
+    REQUIRE(a.mode == 0 || sample_type == PTMB_U8, "PTM_FORMAT_LUM / RGB-input stacks are 8-bit paths");
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (c->probe_next + 1 < c->probe_events.size()) {
         ev0 = c->probe_events[c->probe_next];
@@ -396,7 +408,7 @@ int ptmb_encode_lrgb_dev(ptmb_ctx_t *c, ptmb_xchg_t *x, const void *stack_dev, i
         for (int r = 0; r < a.handoff.world; ++r)
             a.handoff.mailbox[r] = x ? x->mailbox[r] : c->mailbox_dev;
         // the hand-off may only ride on a launch that covers every pixel of the slab
-        const bool mma = ptm::resolve_engine(a.engine, ptm::kDefaultEngineLrgbU8) == 2;
+        const bool mma = a.mode == 0 && ptm::resolve_engine(a.engine, ptm::kDefaultEngineLrgbU8) == 2;
         if (mma && (pixels % 128) % 16 == 0)
             CK(ptm::launch_fit_mma(a, 1, c->sm_count, c->stream, &done));
         if (done == 0 && (pixels % 1024) % 16 == 0)
@@ -459,9 +471,46 @@ int ptmb_probe_read(ptmb_ctx_t *c, float *ms_out, unsigned pairs, unsigned *reco
     return 0;
 }
 
+// ptm_normal (rti-builder/ptmlib.c:808-814) for every pixel: from a float coefficient plane ...
+int ptmb_normal_map(ptmb_ctx_t *c, const float *coeffs_dev, size_t pixels, float *normals_dev) {
+    REQUIRE(c && ((coeffs_dev && normals_dev) || pixels == 0), "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(ptm::launch_normal_map(coeffs_dev, nullptr, ptm::NormalArgs{}, pixels, normals_dev, c->sm_count, c->stream));
+    return 0;
+}
+
+// ... or from a quantised coefficient block, unscaled with the header's scale / bias first (:54)
+int ptmb_normal_map_blocks(ptmb_ctx_t *c, const uint8_t *coef_dev, const float *scale, const int32_t *bias,
+                           size_t pixels, float *normals_dev) {
+    REQUIRE(c && scale && bias && ((coef_dev && normals_dev) || pixels == 0), "NULL argument");
+    ptm::NormalArgs a;
+    memcpy(a.scale, scale, sizeof(a.scale));
+    memcpy(a.bias, bias, sizeof(a.bias));
+    CK(cudaSetDevice(c->device));
+    CK(ptm::launch_normal_map(nullptr, coef_dev, a, pixels, normals_dev, c->sm_count, c->stream));
+    return 0;
+}
+
+// The disabled "L = R + G + B" branch of the reference encoder (rti-builder/ptm-encoder.c:356-400).
+int ptmb_fit_lsum(ptmb_ctx_t *c, const uint8_t *stack_dev, size_t image_stride, size_t pixels, int chroma,
+                  float *coeffs_dev, uint8_t *colour_dev, int32_t *keys_dev) {
+    ptm::FitArgs a;
+    if (make_fit_args(c, stack_dev, image_stride, pixels, a))
+        return 1;
+    REQUIRE(chroma == PTMB_CHROMA_MEAN || chroma == PTMB_CHROMA_MEDIAN, "chroma must be PTMB_CHROMA_MEAN or _MEDIAN");
+    REQUIRE((coeffs_dev && colour_dev && keys_dev) || pixels == 0, "output pointer is NULL");
+    REQUIRE(image_stride >= pixels * 3, "image_stride smaller than one image");
+    a.coeffs = coeffs_dev;
+    a.rgb = colour_dev;
+    a.keys = keys_dev;
+    CK(cudaSetDevice(c->device));
+    CK(ptm::launch_fit_lsum(a, chroma == PTMB_CHROMA_MEDIAN, c->sm_count, c->stream));
+    return 0;
+}
+
 static int relight_common(ptmb_ctx_t *c, ptm::RelightArgs &a, bool lrgb, size_t width, size_t height,
                           const float *scale, const int32_t *bias, const float *uv, unsigned n_dirs,
-                          uint8_t *out_dev) {
+                          uint8_t *out_dev, bool lum = false) {
     REQUIRE(c && scale && bias, "NULL argument");
     REQUIRE((uv && out_dev) || n_dirs == 0, "NULL argument");
     CK(cudaSetDevice(c->device));
@@ -507,9 +556,9 @@ static int relight_common(ptmb_ctx_t *c, ptm::RelightArgs &a, bool lrgb, size_t 
         a.n_dirs = n_dirs - d0 < kBatch ? n_dirs - d0 : kBatch;
         a.light = c->light_dev + (size_t) d0 * PTMB_COEFFICIENTS;
         a.out = out_dev + (size_t) d0 * width * height * 3;
-        cudaError_t e = fast ? ptm::launch_relight_fast(a, lrgb, c->sm_count, c->stream) : cudaErrorNotSupported;
+        cudaError_t e = fast && !lum ? ptm::launch_relight_fast(a, lrgb, c->sm_count, c->stream) : cudaErrorNotSupported;
         if (e == cudaErrorNotSupported)
-            e = ptm::launch_relight(a, lrgb, c->sm_count, c->stream);
+            e = lum ? ptm::launch_relight_lum(a, c->sm_count, c->stream) : ptm::launch_relight(a, lrgb, c->sm_count, c->stream);
         CK(e);
     }
     return 0;
@@ -531,6 +580,18 @@ int ptmb_relight_lrgb(ptmb_ctx_t *c, const uint8_t *coef_dev, const uint8_t *rgb
     a.plane[1] = rgb_dev;
     a.plane[2] = nullptr;
     return relight_common(c, a, true, width, height, scale, bias, uv, n_dirs, out_dev);
+}
+
+// PTM_FORMAT_LUM (rti-builder/ptmlib.c:601-609): rasters are (Y, Cb, Cr) triplets; crcb_dev holds 2-byte
+// (cr, cb) records, the layout the reference's loop reads block 1 with.
+int ptmb_relight_lum(ptmb_ctx_t *c, const uint8_t *coef_dev, const uint8_t *crcb_dev, size_t width, size_t height,
+                     const float *scale, const int32_t *bias, const float *uv, unsigned n_dirs, uint8_t *out_dev) {
+    REQUIRE((coef_dev && crcb_dev) || width * height == 0, "NULL block");
+    ptm::RelightArgs a{};
+    a.plane[0] = coef_dev;
+    a.plane[1] = crcb_dev;
+    a.plane[2] = nullptr;
+    return relight_common(c, a, true, width, height, scale, bias, uv, n_dirs, out_dev, true);
 }
 
 int ptmb_relight_rgb(ptmb_ctx_t *c, const uint8_t *r_dev, const uint8_t *g_dev, const uint8_t *b_dev,
@@ -722,6 +783,8 @@ int ptmb_internal_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, size_t 
         a.coeffs = s.coeffs + px0 * PTMB_COEFFICIENTS;
         if (format_planes == 1) {
             a.rgb = rgb_dev + px0 * 3;
+            a.mode = c->fit_mode;
+            REQUIRE(a.mode == 0 || sample_type == PTMB_U8, "PTM_FORMAT_LUM / RGB-input stacks are 8-bit paths");
             CK(ptm::launch_fit_lrgb(a, sample_type, c->sm_count, c->stream));
         } else {
             a.plane_stride = plane_floats;

@@ -178,7 +178,8 @@ int ptmb_scale_host(ptmb_ctx_t *c, const float *coeffs_host, size_t pixels, int 
 int ptmb_relight_host(ptmb_ctx_t *c, const uint8_t *const *blocks_host, int planes, size_t width, size_t height,
                       const float *scale, const int32_t *bias, const float *uv, unsigned n_dirs,
                       uint8_t *out_host) {
-    REQH(c && blocks_host && scale && bias && (planes == 1 || planes == 3), "bad argument");
+    REQH(c && blocks_host && scale && bias && (planes == 1 || planes == 2 || planes == 3),
+         "bad argument (planes: 1 = LRGB, 2 = LUM, 3 = RGB)");
     REQH((uv && out_host) || n_dirs == 0, "NULL argument");
     CKH(cudaSetDevice(ptmb_internal_device(c)));
     cudaStream_t st = (cudaStream_t) ptmb_internal_stream(c);
@@ -187,10 +188,11 @@ int ptmb_relight_host(ptmb_ctx_t *c, const uint8_t *const *blocks_host, int plan
         return 0;
     DevBuf b0, b1, b2, out;
     CKH(b0.alloc(pixels * 6));
-    CKH(b1.alloc(pixels * (planes == 1 ? 3 : 6)));
+    const size_t b1_bytes = pixels * (planes == 1 ? 3 : planes == 2 ? 2 : 6);   // LUM: 2-byte (cr, cb) records
+    CKH(b1.alloc(b1_bytes));
     CKH(b2.alloc(planes == 3 ? pixels * 6 : 1));
     CKH(cudaMemcpyAsync(b0.p, blocks_host[0], pixels * 6, cudaMemcpyHostToDevice, st));
-    CKH(cudaMemcpyAsync(b1.p, blocks_host[1], pixels * (planes == 1 ? 3 : 6), cudaMemcpyHostToDevice, st));
+    CKH(cudaMemcpyAsync(b1.p, blocks_host[1], b1_bytes, cudaMemcpyHostToDevice, st));
     if (planes == 3)
         CKH(cudaMemcpyAsync(b2.p, blocks_host[2], pixels * 6, cudaMemcpyHostToDevice, st));
     // directions in batches that keep the output staging below ~1 GiB
@@ -201,12 +203,42 @@ int ptmb_relight_host(ptmb_ctx_t *c, const uint8_t *const *blocks_host, int plan
         int rc = planes == 1
                      ? ptmb_relight_lrgb(c, (const uint8_t *) b0.p, (const uint8_t *) b1.p, width, height, scale, bias,
                                          uv + 2 * (size_t) d0, nd, (uint8_t *) out.p)
+                 : planes == 2
+                     ? ptmb_relight_lum(c, (const uint8_t *) b0.p, (const uint8_t *) b1.p, width, height, scale, bias,
+                                        uv + 2 * (size_t) d0, nd, (uint8_t *) out.p)
                      : ptmb_relight_rgb(c, (const uint8_t *) b0.p, (const uint8_t *) b1.p, (const uint8_t *) b2.p, width,
                                         height, scale, bias, uv + 2 * (size_t) d0, nd, (uint8_t *) out.p);
         if (rc)
             return 1;
         CKH(cudaMemcpyAsync(out_host + (size_t) d0 * pixels * 3, out.p, (size_t) nd * pixels * 3,
                             cudaMemcpyDeviceToHost, st));
+        CKH(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+// ptm_normal over a whole PTM with host pointers: exactly one of coeffs_host (float [pixels][6]) and
+// coef_bytes_host (uint8 [pixels][6], unscaled with scale / bias) is given; normals_host float [pixels][3].
+int ptmb_normal_map_host(ptmb_ctx_t *c, const float *coeffs_host, const uint8_t *coef_bytes_host, const float *scale,
+                         const int32_t *bias, size_t pixels, float *normals_host) {
+    REQH(c && normals_host && ((coeffs_host != nullptr) != (coef_bytes_host != nullptr)), "bad argument");
+    REQH(coeffs_host || (scale && bias), "scale / bias needed for a quantised block");
+    CKH(cudaSetDevice(ptmb_internal_device(c)));
+    cudaStream_t st = (cudaStream_t) ptmb_internal_stream(c);
+    const size_t slab = std::min<size_t>(pixels, 4u << 20);
+    const size_t in_px = coeffs_host ? PTMB_COEFFICIENTS * sizeof(float) : PTMB_COEFFICIENTS;
+    DevBuf in, out;
+    CKH(in.alloc(slab * in_px));
+    CKH(out.alloc(slab * 3 * sizeof(float)));
+    for (size_t p0 = 0; p0 < pixels; p0 += slab) {
+        const size_t npx = std::min(slab, pixels - p0);
+        const void *src = coeffs_host ? (const void *) (coeffs_host + p0 * PTMB_COEFFICIENTS)
+                                      : (const void *) (coef_bytes_host + p0 * PTMB_COEFFICIENTS);
+        CKH(cudaMemcpyAsync(in.p, src, npx * in_px, cudaMemcpyHostToDevice, st));
+        if (coeffs_host ? ptmb_normal_map(c, (const float *) in.p, npx, (float *) out.p)
+                        : ptmb_normal_map_blocks(c, (const uint8_t *) in.p, scale, bias, npx, (float *) out.p))
+            return 1;
+        CKH(cudaMemcpyAsync(normals_host + p0 * 3, out.p, npx * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
         CKH(cudaStreamSynchronize(st));
     }
     return 0;

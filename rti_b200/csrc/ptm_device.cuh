@@ -229,6 +229,49 @@ __device__ __forceinline__ void lrgb_finish(unsigned ya, unsigned cba, unsigned 
         c[k] = __fmul_rn(c[k], norm);
 }
 
+// The LUM variant of the same step (rti-builder/ptm-encoder.c:286-305): the averaged YCbCr triplet is
+// stored as it is and the coefficients stay unnormalised.
+__device__ __forceinline__ void lrgb_or_lum_finish(bool lum, unsigned ya, unsigned cba, unsigned cra, float *c,
+                                                   unsigned &r, unsigned &g, unsigned &b) {
+    if (lum) {
+        r = ya;
+        g = cba;
+        b = cra;
+    } else {
+        lrgb_finish(ya, cba, cra, c, r, g, b);
+    }
+}
+
+// RGB -> YCbCr per sample, libjpeg's integer JFIF conversion (jccolor.c rgb_ycc_convert, third party; the
+// reference itself never converts -- its decoder delivers YCbCr, rti-builder/ptm-encoder.c:188 -- so this is the
+// optional front end for RGB-input stacks; oracle/ptm_oracle.c:orc_rgb_to_ycbcr is the
+// same arithmetic on the host):
+//   Y  = ( 19595 R + 38470 G +  7471 B + 32768) >> 16
+//   Cb = (-11059 R - 21709 G + 32768 B + 8388608 + 32767) >> 16
+//   Cr = ( 32768 R - 27439 G -  5329 B + 8388608 + 32767) >> 16         (all sums are positive)
+__device__ __forceinline__ void rgb_to_ycc(unsigned r, unsigned g, unsigned b, unsigned &y, unsigned &cb, unsigned &cr) {
+    y = (19595u * r + 38470u * g + 7471u * b + 32768u) >> 16;
+    cb = (8388608u + 32767u + 32768u * b - 11059u * r - 21709u * g) >> 16;
+    cr = (8388608u + 32767u + 32768u * r - 27439u * g - 5329u * b) >> 16;
+}
+
+// the same on a lane's 12 bytes = 4 interleaved pixels held in three words
+__device__ __forceinline__ void rgb_words_to_ycc(unsigned &w0, unsigned &w1, unsigned &w2) {
+    const unsigned in[3] = {w0, w1, w2};
+    unsigned out[12];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int j = 3 * p;
+        const unsigned r = (in[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+        const unsigned g = (in[(j + 1) >> 2] >> (8 * ((j + 1) & 3))) & 0xFFu;
+        const unsigned b = (in[(j + 2) >> 2] >> (8 * ((j + 2) & 3))) & 0xFFu;
+        rgb_to_ycc(r, g, b, out[j], out[j + 1], out[j + 2]);
+    }
+    w0 = out[0] | (out[1] << 8) | (out[2] << 16) | (out[3] << 24);
+    w1 = out[4] | (out[5] << 8) | (out[6] << 16) | (out[7] << 24);
+    w2 = out[8] | (out[9] << 8) | (out[10] << 16) | (out[11] << 24);
+}
+
 // scale / bias / inverse scale from the extrema (rti-builder/ptmlib.c:858-863).
 __device__ __forceinline__ void scale_bias_from_keys(const int *keys, int k, float &scale, int &bias, float &inv) {
     const float mn = -key_to_float(keys[k]);

@@ -56,7 +56,9 @@ fit_lrgb_u8_kernel(FitArgs a) {
 #pragma unroll 4
         for (unsigned n = 0; n < a.n_lights; ++n) {
             const uint32_t *s = src + (size_t) n * stride_w;
-            const unsigned w0 = __ldg(s), w1 = __ldg(s + 1), w2 = __ldg(s + 2);
+            unsigned w0 = __ldg(s), w1 = __ldg(s + 1), w2 = __ldg(s + 2);
+            if (a.mode & kFitRgbIn)
+                rgb_words_to_ycc(w0, w1, w2);
             const float4 ma = m_s[2 * n], mb = m_s[2 * n + 1];
             const float y[4] = {byte_to_float(w0, PTM_SEL_B0), byte_to_float(w0, PTM_SEL_B3),
                                 byte_to_float(w1, PTM_SEL_B2), byte_to_float(w2, PTM_SEL_B1)};
@@ -87,7 +89,7 @@ fit_lrgb_u8_kernel(FitArgs a) {
             const unsigned ya = div_magic(sum[3 * p], a.magic);
             const unsigned cba = div_magic(sum[3 * p + 1], a.magic);
             const unsigned cra = div_magic(sum[3 * p + 2], a.magic);
-            lrgb_finish(ya, cba, cra, acc[p], out_b[3 * p], out_b[3 * p + 1], out_b[3 * p + 2]);
+            lrgb_or_lum_finish(a.mode & kFitLum, ya, cba, cra, acc[p], out_b[3 * p], out_b[3 * p + 1], out_b[3 * p + 2]);
             ext.add(acc[p]);
         }
         if (kWriteCoeffs) {
@@ -134,7 +136,9 @@ fit_lrgb_generic_kernel(FitArgs a, size_t first_pixel) {
 #pragma unroll 4
         for (unsigned n = 0; n < a.n_lights; ++n) {
             const T *t = reinterpret_cast<const T *>(a.stack + (size_t) n * a.image_stride) + p * 3;
-            const unsigned v0 = __ldg(t), v1 = __ldg(t + 1), v2 = __ldg(t + 2);
+            unsigned v0 = __ldg(t), v1 = __ldg(t + 1), v2 = __ldg(t + 2);
+            if (kShift == 0 && (a.mode & kFitRgbIn))
+                rgb_to_ycc(v0, v1, v2, v0, v1, v2);
             const float y = (float) v0;
 #pragma unroll
             for (int k = 0; k < PTM_NCOEF; ++k)
@@ -146,7 +150,7 @@ fit_lrgb_generic_kernel(FitArgs a, size_t first_pixel) {
         const unsigned ya = s0 / a.n_lights, cba = s1 / a.n_lights, cra = s2 / a.n_lights;
         unsigned r, g, b;
         if (kShift == 0) {
-            lrgb_finish(ya, cba, cra, acc, r, g, b);
+            lrgb_or_lum_finish(a.mode & kFitLum, ya, cba, cra, acc, r, g, b);
         } else {
             float scratch[PTM_NCOEF] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             lrgb_finish(ya >> kShift, cba >> kShift, cra >> kShift, scratch, r, g, b);   // colour only
@@ -413,6 +417,8 @@ cudaError_t launch_fit_lrgb(const FitArgs &a, int sample_type, int sm_count, cud
     if (sample_type != 0 && sample_type != 1)
         return cudaErrorInvalidValue;
     const size_t gen_smem = (size_t) a.n_lights * PTM_NCOEF * sizeof(float);
+    if (a.mode != 0 && sample_type != 0)
+        return cudaErrorNotSupported;   // LUM / RGB-input are 8-bit paths, like the reference's
     if (sample_type == 1) {   // 16-bit stacks: streaming kernel over the tiles, generic kernel for the rest
         size_t done16 = 0;
         cudaError_t e16 = cudaSuccess;
@@ -432,7 +438,7 @@ cudaError_t launch_fit_lrgb(const FitArgs &a, int sample_type, int sm_count, cud
     //    or whole 128-pixel units through the tensor-core kernel
     size_t done = 0;
     cudaError_t e = cudaSuccess;
-    if (resolve_engine(a.engine, kDefaultEngineLrgbU8) == 2)
+    if (a.mode == 0 && resolve_engine(a.engine, kDefaultEngineLrgbU8) == 2)
         e = launch_fit_mma(a, 1, sm_count, st, &done);
     if (e == cudaSuccess && done == 0)
         e = launch_fit_lrgb_tma(a, sm_count, st, &done);

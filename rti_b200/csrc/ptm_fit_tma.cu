@@ -49,10 +49,12 @@ struct TmaSmem {
 
 // One light's contribution to a lane's four pixels.
 //   word0 = Y0 Cb0 Cr0 Y1 | word1 = Cb1 Cr1 Y2 Cb2 | word2 = Cr2 Y3 Cb3 Cr3
-template <bool kSums = true>
+template <bool kSums = true, bool kRgbIn = false>
 __device__ __forceinline__ void consume_light(const uint32_t *s32, const float4 *m, float (&acc)[4][PTM_NCOEF],
                                               unsigned (&ev)[3], unsigned (&od)[3]) {
-    const unsigned w0 = s32[0], w1 = s32[1], w2 = s32[2];
+    unsigned w0 = s32[0], w1 = s32[1], w2 = s32[2];
+    if (kRgbIn)
+        rgb_words_to_ycc(w0, w1, w2);   // RGB-input stacks: per-sample integer JFIF conversion first
     const float4 ma = m[0], mb = m[1];
     const float y[4] = {byte_to_float(w0, PTM_SEL_B0), byte_to_float(w0, PTM_SEL_B3),
                         byte_to_float(w1, PTM_SEL_B2), byte_to_float(w2, PTM_SEL_B1)};
@@ -124,7 +126,7 @@ __device__ __forceinline__ void cta_stamp(int slot) {
 #define PTM_STAMP(slot)
 #endif
 
-template <int L, int S, bool kWriteCoeffs, bool kFull, int kDebug = 0>
+template <int L, int S, bool kWriteCoeffs, bool kFull, int kDebug = 0, bool kRgbIn = false>
 __global__ void __launch_bounds__(kTmaThreads, 2)
 fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
     using Smem = TmaSmem<L, S>;
@@ -256,6 +258,9 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
                 const unsigned cnt = kFull ? (unsigned) L : min((unsigned) L, n - l0);
                 if (kDebug == 1) {
                     ev[0] += buf[0];
+                } else if (kRgbIn) {
+                    for (unsigned l = 0; l < cnt; ++l)
+                        consume_light<true, true>(buf + l * (kTileBytes / 4), m_s + 2 * (l0 + l), acc, ev, od);
                 } else if (cnt == L) {
                     // straight-line body: all loads of the stage can be hoisted; byte sums go pairwise
 #pragma unroll
@@ -298,7 +303,7 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
                 const unsigned ya = div_magic(sum[3 * p], a.magic);
                 const unsigned cba = div_magic(sum[3 * p + 1], a.magic);
                 const unsigned cra = div_magic(sum[3 * p + 2], a.magic);
-                lrgb_finish(ya, cba, cra, acc[p], out_b[3 * p], out_b[3 * p + 1], out_b[3 * p + 2]);
+                lrgb_or_lum_finish(a.mode & kFitLum, ya, cba, cra, acc[p], out_b[3 * p], out_b[3 * p + 1], out_b[3 * p + 2]);
             }
             if (4 * t < tile_px_of(tile, n_tiles, tail_px))   // lanes past a partial tile hold stale bytes
                 ext.add4(acc);
@@ -361,7 +366,7 @@ static cudaError_t launch_variant(const FitArgs &a, size_t n_tiles, unsigned tai
     using Smem = TmaSmem<L, S>;
     static_assert(L <= 32, "one producer lane per light of a stage");
     // opt in to > 48 KB of dynamic shared memory and look up residency, once per device
-    static int per_sm_cache[64][4];
+    static int per_sm_cache[64][5];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess)
@@ -372,7 +377,13 @@ static cudaError_t launch_variant(const FitArgs &a, size_t n_tiles, unsigned tai
     const bool full = a.n_lights % L == 0;
     auto kern = wc ? (full ? fit_lrgb_u8_tma_kernel<L, S, true, true, kDebug> : fit_lrgb_u8_tma_kernel<L, S, true, false, kDebug>)
                    : (full ? fit_lrgb_u8_tma_kernel<L, S, false, true, kDebug> : fit_lrgb_u8_tma_kernel<L, S, false, false, kDebug>);
-    const int slot = wc * 2 + (full ? 1 : 0);
+    int slot = wc * 2 + (full ? 1 : 0);
+    if (a.mode & kFitRgbIn) {   // RGB-input stacks: the instantiation with the per-sample colour conversion
+        kern = fit_lrgb_u8_tma_kernel<L, S, true, false, 0, true>;
+        slot = 4;
+        if (!wc)
+            return cudaErrorNotSupported;
+    }
     if (per_sm_cache[dev][slot] == 0) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Smem::total(257));
         if (e != cudaSuccess)
@@ -640,7 +651,7 @@ cudaError_t launch_fit_lrgb_tma(const FitArgs &a, int sm_count, cudaStream_t st,
     const unsigned rem = (unsigned) (a.pixels % kTilePx);
     const unsigned tail_px = (rem % 16 == 0) ? rem : 0;
     const size_t n_tiles = full_tiles + (tail_px ? 1 : 0);
-    if (!ok || n_tiles == 0 || n_tiles > 0xFFFFFFFFull)
+    if (!ok || n_tiles == 0 || n_tiles > 0xFFFFFFFFull || ((a.mode & kFitRgbIn) && !a.coeffs))
         return cudaSuccess;
     static int variant = -1;
     if (variant < 0) {

@@ -49,6 +49,7 @@ struct ptmb_ctx {
     unsigned kpad = 0;
     int engine = 0;
     int relight_mode = 0;                    // PTMB_RELIGHT_*
+    int fit_mode = 0;                        // PTMB_FIT_* flags of the LRGB-shaped entries
     int *keys_dev = nullptr;                 // scratch for the host-buffer entry points
     ptmb_scale_bias_t *sb_dev = nullptr;
     std::vector<float> light_host;

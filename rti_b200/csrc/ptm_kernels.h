@@ -60,7 +60,13 @@ struct FitArgs {
     // float plane is what K2 reads next; kept with priority, part of it is still in L2 then)
     int store_hint;
     int engine;             // PTMB_ENGINE_*: 0 = default choice, 1 = FFMA kernels, 2 = tensor-core kernel
+    // LRGB-shaped fits only: kFitLum = PTM_FORMAT_LUM (no colour conversion, no normalisation: the colour block
+    // is the averaged YCbCr triplet), kFitRgbIn = the stack holds RGB triplets that are converted to YCbCr per
+    // sample (libjpeg's integer formula) before anything else.  Both are served by the FFMA kernels.
+    int mode;
 };
+constexpr int kFitLum = 1;
+constexpr int kFitRgbIn = 2;
 
 struct RelightArgs {
     const uint8_t *plane[3];  // LRGB: coef, rgb, unused; RGB: r, g, b coefficient planes
@@ -71,6 +77,15 @@ struct RelightArgs {
     unsigned n_dirs;
     uint8_t *out;             // [n_dirs][height][width][3]
 };
+
+struct NormalArgs {
+    float scale[6];
+    int bias[6];
+};
+cudaError_t launch_normal_map(const float *coeffs, const uint8_t *bytes, const NormalArgs &a, size_t pixels,
+                              float *normals, int sm_count, cudaStream_t st);
+cudaError_t launch_relight_lum(const RelightArgs &a, int sm_count, cudaStream_t st);
+cudaError_t launch_fit_lsum(const FitArgs &a, bool median, int sm_count, cudaStream_t st);
 
 bool pack_mma_digits(const float *M, unsigned n_lights, std::vector<int8_t> &image, float *scale, unsigned *kpad_out);
 // per-format default engines (1 = FFMA kernels, 2 = tensor-core kernel), see DESIGN.md

@@ -263,6 +263,15 @@ int ptmb_multi_set_matrix(ptmb_multi_t *m, const float *M, unsigned n_lights) {
     return m->run_all([=](int i) { return ptmb_set_matrix(m->ctx[i], M, n_lights); });
 }
 
+int ptmb_multi_set_fit_mode(ptmb_multi_t *m, int flags) {
+    if (!m)
+        return ptmb_internal_fail("ptmb_multi_set_fit_mode", "NULL argument");
+    for (int i = 0; i < m->n; ++i)
+        if (ptmb_set_fit_mode(m->ctx[i], flags))
+            return 1;
+    return 0;
+}
+
 int ptmb_multi_synchronize(ptmb_multi_t *m) {
     if (!m)
         return ptmb_internal_fail("ptmb_multi_synchronize", "NULL argument");

@@ -231,6 +231,13 @@ ptm_header_t *ptm_read_header (FILE *fp) {
     get_sizes (fp, 2, h->dimen);
     get_floats (fp, PTM_COEFFICIENTS, h->scale);
     get_ints (fp, PTM_COEFFICIENTS, h->bias);
+    if (format->id == PTM_FORMAT_LUM) {
+        /* ptm_write_header emits the 4 x 4 colour matrix for LUM (ref :225-227) but the reference's reader
+         * never consumes it (its LUM round trip is broken); read it here so that
+         * the payload starts where the writer put it */
+        float matrix[16];
+        get_floats (fp, 16, matrix);
+    }
     if (format->jpeg_streams) {
         const int n = format->jpeg_streams;
         get_ints (fp, 1, h->compression_param);
@@ -274,6 +281,24 @@ void ptm_write_header (FILE *fp, const ptm_header_t *h) {
 /* ref :319-324 */
 static void read_plain_blocks (FILE *fp, const ptm_header_t *h, ptm_block_t *blocks) {
     const size_t pixels = h->dimen[0] * h->dimen[1];
+    if (h->format->id == PTM_FORMAT_LUM) {
+        /* the writer's layout (ref :333-347): per pixel six coefficients, then Cr, Cb.  The reference reads
+         * this as two planar blocks (ref :319-324), which cannot work; here the records are taken apart:
+         * block 0 = coefficients, block 1 = 2-byte (cr, cb) records -- the layout the relight loop
+         * (ref :601-609) addresses block 1 with */
+        JSAMPLE *c = blocks[0], *crcb = blocks[1];
+        for (size_t p = 0; p < pixels; ++p, c += PTM_COEFFICIENTS, crcb += CBCR_COEFFICIENTS) {
+            JSAMPLE rec[PTM_COEFFICIENTS + CBCR_COEFFICIENTS];
+            if (fread (rec, sizeof (rec), 1, fp) != 1) {
+                fprintf (stderr, "short read in PTM block 0\n");
+                break;
+            }
+            memcpy (c, rec, PTM_COEFFICIENTS);
+            crcb[0] = rec[PTM_COEFFICIENTS];
+            crcb[1] = rec[PTM_COEFFICIENTS + 1];
+        }
+        return;
+    }
     for (int i = 0; i < h->format->blocks; ++i) {
         if (fread (blocks[i], sample_bytes (h, i), pixels, fp) != pixels)
             fprintf (stderr, "short read in PTM block %d\n", i);
@@ -521,16 +546,12 @@ void ptm_scale_coefficients (ptm_header_t *h, const ptm_unscaled_coefficients_t 
 void ptm_encode_stack (ptm_header_t *h, const ptm_image_info_t *info, const JSAMPLE *buffer,
                        const float *M, ptm_block_t *blocks) {
     ptmb_scale_bias_t sb;
-    if (h->format->color_components == 2) {
-        /* LUM (rti-builder/ptm-encoder.c:286-305): fit Y, average the triplets, no normalisation */
-        ptm_unscaled_coefficients_t *coeffs = calloc (info->pixels, sizeof (*coeffs));
-        ptm_fit_poly_jsample (info, buffer, 3, M, coeffs);
-        ptm_cbcr_avg (info, (const ycbcr_coefficients_t *) buffer, (ycbcr_coefficients_t *) blocks[1]);
-        ptm_scale_coefficients (h, coeffs, blocks);
-        free (coeffs);
-        return;
-    }
+    /* LUM (rti-builder/ptm-encoder.c:286-305): fit Y, average the triplets, no colour conversion and no
+     * normalisation -- the same fused pass with PTMB_FIT_LUM */
+    const int lum = h->format->color_components == 2;
     ptmb_multi_t *multi = gpu_multi ();
+    if (multi ? ptmb_multi_set_fit_mode (multi, lum ? PTMB_FIT_LUM : 0) : ptmb_set_fit_mode (gpu (), lum ? PTMB_FIT_LUM : 0))
+        gpu_die ("ptmb_set_fit_mode");
     if (multi) {
         if (ptmb_multi_encode_host (multi, buffer, PTMB_U8, info->width, info->height, info->n_decoders, M,
                                     h->format->ptm_blocks, blocks, NULL, &sb))
@@ -564,7 +585,7 @@ int ptm_encode_jpeg_files (ptm_header_t *h, const ptm_image_info_t *info, const 
         ptmb_malloc (ctx, pixels * 6 * planes + pixels * 3, &bytes) || ptmb_malloc (ctx, sizeof (ptmb_scale_bias_t), &sb) ||
         ptmb_malloc (ctx, PTMB_KEYS * sizeof (int32_t), &keys))
         goto done;
-    if (ptmb_set_matrix (ctx, M, (unsigned) n))
+    if (ptmb_set_matrix (ctx, M, (unsigned) n) || ptmb_set_fit_mode (ctx, 0))
         goto done;
     for (size_t i = 0; i < n; ++i) {
         unsigned w = 0, hgt = 0, c = 0;
@@ -616,12 +637,9 @@ void ptm_relight_batch (const ptm_header_t *h, ptm_block_t *blocks, const float 
     int32_t bias[PTM_COEFFICIENTS];
     for (int i = 0; i < PTM_COEFFICIENTS; ++i)
         bias[i] = h->bias[i];
-    if (h->format->color_components == 2) {
-        fprintf (stderr, "ptmlib (B200): relighting PTM_FORMAT_LUM is not supported "
-                         "(the reference marks it untested, rti-builder/ptmlib.c:601)\n");
-        exit (1);
-    }
-    if (ptmb_relight_host (gpu (), (const uint8_t *const *) blocks, h->format->ptm_blocks, h->dimen[0],
+    /* PTM_FORMAT_LUM (ref :601-609): a YCbCr raster, block 1 addressed as (cr, cb) records */
+    const int planes = h->format->color_components == 2 ? 2 : h->format->ptm_blocks;
+    if (ptmb_relight_host (gpu (), (const uint8_t *const *) blocks, planes, h->dimen[0],
                            h->dimen[1], h->scale, bias, uv, n_dirs, out))
         gpu_die ("ptm_relight");
 }
@@ -636,9 +654,9 @@ void ptm_write_jpeg (FILE *fp, const ptm_header_t *h, ptm_block_t *blocks, float
     const size_t pixels = h->dimen[0] * h->dimen[1];
     JSAMPLE *raster = malloc (pixels > 0 ? pixels * 3 : 1);
     ptm_relight (h, blocks, u, v, raster);
-    /* quality from the header, RGB colour space (ref :575-577; LUM would be YCbCr) */
-    if (ptm_codec_write (fp, raster, (unsigned int) h->dimen[0], (unsigned int) h->dimen[1], 3, 0,
-                         h->compression_param[0]))
+    /* quality from the header; RGB colour space, YCbCr for LUM (ref :575-577) */
+    if (ptm_codec_write (fp, raster, (unsigned int) h->dimen[0], (unsigned int) h->dimen[1], 3,
+                         h->format->color_components == 2, h->compression_param[0]))
         fprintf (stderr, "cannot write image\n");
     free (raster);
 }
@@ -651,6 +669,14 @@ void ptm_normal (const ptm_unscaled_coefficients_t *c, float *nu, float *nv, flo
     *nu = (c->cuv * c->cv - 2 * c->cv2 * c->cu) / divisor;
     *nv = (c->cuv * c->cu - 2 * c->cu2 * c->cv) / divisor;
     *nw = sqrtf (1.0f - *nu * *nu + *nv * *nv);
+}
+
+void ptm_normal_map (const ptm_header_t *h, ptm_block_t *blocks, float *normals) {
+    int32_t bias[PTM_COEFFICIENTS];
+    for (int i = 0; i < PTM_COEFFICIENTS; ++i)
+        bias[i] = h->bias[i];
+    if (ptmb_normal_map_host (gpu (), NULL, blocks[0], h->scale, bias, h->dimen[0] * h->dimen[1], normals))
+        gpu_die ("ptm_normal_map");
 }
 
 /* ref :883-891 */

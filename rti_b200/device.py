@@ -91,6 +91,11 @@ class Context:
         code = {"default": 0, "ffma": 1, "mma": 2}[engine] if isinstance(engine, str) else int(engine)
         _lib.check(self._lib.ptmb_set_fit_engine(self._h, code))
 
+    def set_fit_mode(self, lum=False, rgb_input=False):
+        """Variants of the LRGB-shaped entries: lum = PTM_FORMAT_LUM (colour block = mean YCbCr, no
+        normalisation); rgb_input = the stack holds RGB triplets, converted to YCbCr per sample inside K1."""
+        _lib.check(self._lib.ptmb_set_fit_mode(self._h, (1 if lum else 0) | (2 if rgb_input else 0)))
+
     def set_relight_mode(self, mode):
         """"auto" (exact below 4 directions, else fast) | "exact" (bit-identical to the reference decoder) |
         "fast" (every byte within +-1, HBM-rate sweeps)."""
@@ -160,6 +165,29 @@ class Context:
         _lib.check(self._lib.ptmb_relight_rgb(self._h, _ptr(r), _ptr(g), _ptr(b), width, height,
                                               scale.ctypes.data, bias.ctypes.data, uv.ctypes.data, uv.shape[0],
                                               _ptr(out)))
+
+    def relight_lum(self, coef, crcb, width, height, scale, bias, uv, out):
+        """PTM_FORMAT_LUM: (Y, Cb, Cr) rasters; crcb = 2-byte (cr, cb) records."""
+        scale = np.ascontiguousarray(scale, dtype=np.float32)
+        bias = np.ascontiguousarray(bias, dtype=np.int32)
+        uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+        _lib.check(self._lib.ptmb_relight_lum(self._h, _ptr(coef), _ptr(crcb), width, height, scale.ctypes.data,
+                                              bias.ctypes.data, uv.ctypes.data, uv.shape[0], _ptr(out)))
+
+    def normal_map(self, coeffs, pixels, normals):
+        """float coefficient plane [pixels][6] -> normals float [pixels][3]."""
+        _lib.check(self._lib.ptmb_normal_map(self._h, _ptr(coeffs), pixels, _ptr(normals)))
+
+    def normal_map_blocks(self, coef_bytes, scale, bias, pixels, normals):
+        scale = np.ascontiguousarray(scale, dtype=np.float32)
+        bias = np.ascontiguousarray(bias, dtype=np.int32)
+        _lib.check(self._lib.ptmb_normal_map_blocks(self._h, _ptr(coef_bytes), scale.ctypes.data, bias.ctypes.data,
+                                                    pixels, _ptr(normals)))
+
+    def fit_lsum(self, stack, image_stride, pixels, coeffs, colour, keys, median=False):
+        """The reference encoder's disabled L = R + G + B branch; median=True: median chroma instead of the mean."""
+        _lib.check(self._lib.ptmb_fit_lsum(self._h, _ptr(stack), image_stride, pixels, 1 if median else 0,
+                                           _ptr(coeffs), _ptr(colour), _ptr(keys)))
 
     def jpeg_info(self, data):
         w, h, c = C.c_uint(0), C.c_uint(0), C.c_uint(0)

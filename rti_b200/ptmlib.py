@@ -67,6 +67,8 @@ def lib():
                                        C.POINTER(C.c_void_p)]
         L.ptm_relight.argtypes = [C.POINTER(PtmHeader), C.POINTER(C.c_void_p), C.c_float, C.c_float, C.c_void_p]
         L.ptm_normal.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ptm_normal_map.argtypes = [C.POINTER(PtmHeader), C.POINTER(C.c_void_p), C.c_void_p]
+        L.ptm_normal_map.restype = None
         for f in ("ptm_fit_poly_jsample", "ptm_fit_poly_uint", "ptm_cbcr_avg", "ptm_lrgb_finish",
                   "ptm_scale_coefficients", "ptm_encode_stack", "ptm_relight", "ptm_normal"):
             getattr(L, f).restype = None
@@ -173,6 +175,13 @@ def ptm_encode_stack(header, info, buffer, M, blocks):
 def ptm_relight(header, blocks, u, v):
     out = np.empty((header.dimen[1], header.dimen[0], 3), np.uint8)
     lib().ptm_relight(C.byref(header), _block_ptrs(blocks), u, v, out.ctypes.data)
+    return out
+
+
+def ptm_normal_map(header, blocks):
+    """ptm_normal for every pixel of a PTM's first coefficient block -> float32 [pixels][3]."""
+    out = np.empty((header.dimen[0] * header.dimen[1], 3), np.float32)
+    lib().ptm_normal_map(C.byref(header), _block_ptrs(blocks), out.ctypes.data)
     return out
 
 

@@ -151,3 +151,71 @@ def test_oracle_vs_reference_live(oracle, dome1, M60):
         np.testing.assert_array_equal(ref["bias"], enc["bias"])
         np.testing.assert_array_equal(oracle.ref_decode(path, 0.2, -0.4),
                                       oracle.relight_rgb(np.stack(ref["blocks"]), ref["scale"], ref["bias"], 0.2, -0.4))
+
+
+# ------------------------------------------------------------------ round 2: f-4 pieces and the RGB front end
+
+def test_rgb_to_ycbcr_is_the_jfif_conversion(oracle):
+    """orc_rgb_to_ycbcr restates libjpeg's integer converter (third party, absent from the reference tree): known
+    triplets, and within 1 of the real-valued JFIF matrix for every corner / random colour."""
+    known = {(255, 255, 255): (255, 128, 128), (0, 0, 0): (0, 128, 128), (255, 0, 0): (76, 85, 255),
+             (0, 255, 0): (150, 44, 21), (0, 0, 255): (29, 255, 107), (128, 128, 128): (128, 128, 128)}
+    for rgb, ycc in known.items():
+        got = oracle.rgb_to_ycbcr(np.array(rgb, np.uint8).reshape(1, 1, 1, 3)).reshape(3)
+        assert tuple(int(x) for x in got) == ycc, (rgb, got)
+    rng = np.random.default_rng(1)
+    rgb = rng.integers(0, 256, (1, 64, 64, 3), dtype=np.uint8)
+    got = oracle.rgb_to_ycbcr(rgb).astype(np.float64)
+    r, g, b = (rgb[..., i].astype(np.float64) for i in range(3))
+    want = np.stack([0.299 * r + 0.587 * g + 0.114 * b,
+                     -0.168735892 * r - 0.331264108 * g + 0.5 * b + 128,
+                     0.5 * r - 0.418687589 * g - 0.081312411 * b + 128], -1)
+    assert np.abs(got - np.clip(want, 0, 255)).max() <= 1.0
+
+
+def test_lum_relight_and_normal_map_restatements(oracle, dome1, M60):
+    """orc_relight_lum against a plain numpy statement of rti-builder/ptmlib.c:601-609, orc_normal_map against
+    the scalar orc_normal (which tests/golden pins)."""
+    rng = np.random.default_rng(2)
+    W, H = 9, 5
+    coef = rng.integers(0, 256, (H, W, 6), dtype=np.uint8)
+    crcb = rng.integers(0, 256, (H, W, 2), dtype=np.uint8)
+    scale = np.array([0.9, 1.1, 0.7, 1.3, 0.8, 1.0], np.float32)
+    bias = np.array([120, 131, 117, 125, 140, 10], np.int32)
+    u, v = np.float32(0.3), np.float32(-0.6)
+    got = oracle.relight_lum(coef, crcb, scale, bias, float(u), float(v))
+    light = [u * u, v * v, u * v, u, v]
+    for y in range(H):
+        for x in range(W):
+            c = coef[H - 1 - y, x].astype(np.int32)
+            s = np.float32(0)
+            for k in range(5):
+                term = np.float32(np.float32(scale[k] * np.float32(c[k] - bias[k])) * light[k])
+                s = term if k == 0 else np.float32(s + term)
+            s = np.float32(s + np.float32(scale[5] * np.float32(c[5] - bias[5])))
+            want_y = 255 if s > 255 else (0 if s < 0 else int(s))
+            assert tuple(got[y, x]) == (want_y, crcb[H - 1 - y, x, 1], crcb[H - 1 - y, x, 0])
+    coeffs = rng.normal(0, 50, (20, 6)).astype(np.float32)
+    nm = oracle.normal_map(coeffs=coeffs)
+    for p in range(20):
+        want = np.array(oracle.normal(coeffs[p]), np.float32)
+        assert np.array_equal(nm[p], want, equal_nan=True)
+
+
+def test_lsum_branch_restatement(oracle, dome1, M60):
+    """orc_fit_lsum: mean chroma = ptm_cbcr_avg's truncated mean scaled by 256 / L_0; the median option is the
+    textbook median ((lower + upper middle) / 2)."""
+    stack = oracle.synth_stack(9, 1, 7, 5, dome1)
+    mean = oracle.fit_lsum(stack, M60, median=False)
+    med = oracle.fit_lsum(stack, M60, median=True)
+    L0 = stack[0].astype(np.int64).sum(-1)
+    avg = stack.astype(np.int64).sum(0) // stack.shape[0]
+    np.testing.assert_array_equal(mean["colour"], ((256 * avg) // L0[..., None]).astype(np.uint8))
+    m = np.sort(stack.astype(np.int64), 0)
+    n = stack.shape[0]
+    mid = (m[(n - 1) // 2] + m[n // 2]) // 2
+    np.testing.assert_array_equal(med["colour"], ((256 * mid) // L0[..., None]).astype(np.uint8))
+    np.testing.assert_array_equal(mean["coeffs"], med["coeffs"])
+    # the fit is ptm_fit_poly_uint on L = R + G + B
+    L = stack.astype(np.uint32).sum(-1, dtype=np.uint32)[..., None]
+    np.testing.assert_array_equal(mean["coeffs"], oracle.fit_u32(np.ascontiguousarray(L), M60, 0))
