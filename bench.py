@@ -408,6 +408,7 @@ def run_dropin(stack_np, L, want_blocks):
     from rti_b200 import ptmlib
     n, H, W, _ = stack_np.shape
     M = ptmlib.ptm_svd(L)
+    stack_np = np.array(stack_np, copy=True)               # a plain malloc'd (pageable) copy, like the reference's buffer
 
     def once():
         t0 = time.perf_counter()

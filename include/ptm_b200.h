@@ -302,6 +302,14 @@ int ptmb_multi_encode_lrgb_dev (ptmb_multi_t *multi, const void *const *stack_de
                                 uint8_t *const *rgb_dev, uint8_t *const *coef_bytes_dev,
                                 ptmb_scale_bias_t *const *sb_dev);
 
+/* A promise by the caller about the stacks it passes to ptmb_encode_lrgb_dev: nothing queued earlier on the
+ * context's stream writes them (they were complete before the PREVIOUS call on the stream was enqueued -- e.g. a
+ * resident stack encoded repeatedly, or slabs uploaded on another stream and joined by an event earlier on).
+ * K1 is launched programmatically dependent on the previous kernel; with the promise its copy engine warp
+ * starts streaming the stack while that kernel still drains (a few microseconds per encode, which matters when
+ * an 8-GPU slab takes 0.12 ms).  Default 0: K1 waits for the previous kernel before it reads anything. */
+int ptmb_set_stack_stable (ptmb_ctx_t *ctx, int stable);
+
 /* Timing probes for benchmarks: the next `pairs` ptmb_encode_lrgb_dev calls bracket their fit
  * stage with CUDA events on the context's stream; _read synchronises and returns milliseconds. */
 int ptmb_probe_arm (ptmb_ctx_t *ctx, unsigned pairs);

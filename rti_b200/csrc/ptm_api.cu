@@ -9,6 +9,7 @@
 
 #include "../../include/ptm_b200.h"
 #include "ptm_device.cuh"
+#include "ptm_hostpipe.h"
 #include "ptm_internal.h"
 #include "ptm_kernels.h"
 
@@ -100,6 +101,10 @@ int ptmb_create(int device, void *stream, ptmb_ctx_t **out) {
 }
 
 static void encode_scratch_release(ptmb_ctx *c);
+extern "C" void ptmb_internal_host_release(ptmb_ctx_t *c);
+ptm::HostState **ptmb_internal_host(ptmb_ctx_t *c) { return &c->host; }
+int ptmb_internal_host_threads(const ptmb_ctx_t *c) { return c->host_threads; }
+void ptmb_internal_set_host_threads(ptmb_ctx_t *c, int n) { c->host_threads = n; }
 
 void ptmb_destroy(ptmb_ctx_t *c) {
     if (!c)
@@ -107,6 +112,7 @@ void ptmb_destroy(ptmb_ctx_t *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     encode_scratch_release(c);
+    ptmb_internal_host_release(c);
     cudaFree(c->M_dev);
     cudaFree(c->digits_dev);
     cudaFree(c->keys_dev);
@@ -259,6 +265,7 @@ static int make_fit_args(ptmb_ctx_t *c, const void *stack_dev, size_t image_stri
     a.kpad = c->kpad;
     a.engine = c->engine;
     a.mode = 0;   // the LRGB-shaped entries set it from the context (ptmb_set_fit_mode)
+    a.stack_stable = 0;
     a.tile_counter = c->ticket_dev ? c->ticket_dev + 1 : nullptr;
     static int store_hint = -1;
     if (store_hint < 0) {
@@ -285,6 +292,12 @@ int ptmb_fit_lrgb(ptmb_ctx_t *c, const void *stack_dev, int sample_type, size_t 
     REQUIRE(a.mode == 0 || sample_type == PTMB_U8, "PTM_FORMAT_LUM / RGB-input stacks are 8-bit paths");
     CK(cudaSetDevice(c->device));
     CK(ptm::launch_fit_lrgb(a, sample_type, c->sm_count, c->stream));
+    return 0;
+}
+
+int ptmb_set_stack_stable(ptmb_ctx_t *c, int stable) {
+    REQUIRE(c, "ctx is NULL");
+    c->stack_stable = stable != 0;
     return 0;
 }
 
@@ -386,6 +399,7 @@ int ptmb_encode_lrgb_dev(ptmb_ctx_t *c, ptmb_xchg_t *x, const void *stack_dev, i
     a.rgb = rgb_dev;
     a.keys = c->keys_dev;   // kept at the initial extrema between encodes (reset by the hand-off)
     a.mode = c->fit_mode;
+    a.stack_stable = c->stack_stable;
     REQUIRE(a.mode == 0 || sample_type == PTMB_U8, "PTM_FORMAT_LUM / RGB-input stacks are 8-bit paths");
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (c->probe_next + 1 < c->probe_events.size()) {
@@ -766,14 +780,27 @@ int ptmb_internal_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, size_t 
     uint8_t *rgb_dev = s.bytes + pixels * PTMB_COEFFICIENTS * format_planes;
 
     CK(ptm::launch_keys_init(c->keys_dev, c->stream));
+    // pageable operands go through the staging pipe (ptm_hostpipe.h); pinned ones are copied directly
+    ptm::HostPipe *pipe = nullptr, *pipe_back = nullptr;
+    if (!ptm::HostPipe::is_pinned(stack_host) || (early && !ptm::HostPipe::is_pinned(early))) {
+        ptm::HostState *hs = ptm::host_state(c);
+        if (hs) {
+            pipe = ptm::HostPipe::is_pinned(stack_host) ? nullptr : &hs->pipe;
+            pipe_back = (early && !ptm::HostPipe::is_pinned(early)) ? &hs->pipe : nullptr;
+        }
+    }
     int buf = 0;
     for (size_t row = 0; row < height; row += slab_rows, buf ^= 1) {
         const size_t rows = height - row < slab_rows ? height - row : slab_rows;
         const size_t px0 = row * width, npx = rows * width;
         CK(cudaStreamWaitEvent(s.copy, s.consumed[buf], 0));
         // one strided copy per slab: n_lights rows of npx * 3 * ss bytes, host pitch = one image
-        CK(cudaMemcpy2DAsync(s.stage[buf], slab_stride, (const uint8_t *) stack_host + px0 * 3 * ss, image_bytes,
-                             npx * 3 * ss, n_lights, cudaMemcpyHostToDevice, s.copy));
+        if (pipe)   // pageable stack: staged through the pinned ring by the host thread pool
+            CK(pipe->h2d_2d(s.stage[buf], slab_stride, (const uint8_t *) stack_host + px0 * 3 * ss, image_bytes,
+                            npx * 3 * ss, n_lights, s.copy));
+        else
+            CK(cudaMemcpy2DAsync(s.stage[buf], slab_stride, (const uint8_t *) stack_host + px0 * 3 * ss, image_bytes,
+                                 npx * 3 * ss, n_lights, cudaMemcpyHostToDevice, s.copy));
         CK(cudaEventRecord(s.copied[buf], s.copy));
         CK(cudaStreamWaitEvent(c->stream, s.copied[buf], 0));
         ptm::FitArgs a;
@@ -794,7 +821,10 @@ int ptmb_internal_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, size_t 
         if (early) {
             // this slab's RGB bytes are final: send them home while the next slabs arrive
             CK(cudaStreamWaitEvent(s.back, s.consumed[buf], 0));
-            CK(cudaMemcpyAsync(early + px0 * 3, rgb_dev + px0 * 3, npx * 3, cudaMemcpyDeviceToHost, s.back));
+            if (pipe_back)
+                CK(pipe_back->d2h(early + px0 * 3, rgb_dev + px0 * 3, npx * 3, s.back));
+            else
+                CK(cudaMemcpyAsync(early + px0 * 3, rgb_dev + px0 * 3, npx * 3, cudaMemcpyDeviceToHost, s.back));
         }
     }
     if (early) {
@@ -828,21 +858,33 @@ int ptmb_internal_encode_host_finish(ptmb_ctx_t *c, const int32_t *keys_dev, uin
         CK(ptm::launch_quantise(s.coeffs + b * plane_floats, pixels, ptm::KeySource{keys, nullptr, 0, 0},
                                 s.bytes + (size_t) b * pixels * PTMB_COEFFICIENTS, b == 0 ? c->sb_dev : nullptr,
                                 coeffs_host == nullptr, c->sm_count, c->stream));
+    // device -> host: direct for pinned destinations, through the staging pipe for pageable ones
+    ptm::HostState *hs = c->host;
+    auto to_host = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+        if (!ptm::HostPipe::is_pinned(dst) && (hs || (hs = ptm::host_state(c))))
+            return hs->pipe.d2h(dst, src, bytes, c->stream);
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream);
+    };
     for (int b = 0; b < s.planes; ++b)
-        CK(cudaMemcpyAsync(blocks_host[b], s.bytes + (size_t) b * pixels * PTMB_COEFFICIENTS,
-                           pixels * PTMB_COEFFICIENTS, cudaMemcpyDeviceToHost, c->stream));
+        CK(to_host(blocks_host[b], s.bytes + (size_t) b * pixels * PTMB_COEFFICIENTS, pixels * PTMB_COEFFICIENTS));
     if (s.planes == 1) {
         if (s.early_rgb_done && s.early_rgb_done == blocks_host[1])
             CK(cudaStreamWaitEvent(c->stream, s.fitted, 0));   // already on its way / there
         else
-            CK(cudaMemcpyAsync(blocks_host[1], rgb_dev, pixels * 3, cudaMemcpyDeviceToHost, c->stream));
+            CK(to_host(blocks_host[1], rgb_dev, pixels * 3));
     }
     if (coeffs_host)
         for (int b = 0; b < s.planes; ++b)
-            CK(cudaMemcpyAsync(coeffs_host + (size_t) b * (coeffs_plane_floats ? coeffs_plane_floats : plane_floats),
-                               s.coeffs + (size_t) b * plane_floats, plane_floats * sizeof(float),
-                               cudaMemcpyDeviceToHost, c->stream));
+            CK(to_host(coeffs_host + (size_t) b * (coeffs_plane_floats ? coeffs_plane_floats : plane_floats),
+                       s.coeffs + (size_t) b * plane_floats, plane_floats * sizeof(float)));
     CK(cudaMemcpyAsync(sb_host, c->sb_dev, sizeof(ptmb_scale_bias_t), cudaMemcpyDeviceToHost, c->stream));
+    // invariant of the context: its own keys are at the initial extrema between calls (the fused device
+    // encode merges into them without a keys-init launch of its own)
+    CK(ptm::launch_keys_init(c->keys_dev, c->stream));
+    if (c->host && c->host->pipe_ok)
+        CK(c->host->pipe.finish());   // pageable destinations: the last staged chunks reach the caller's buffers
+    if (s.early_rgb_done && s.back)
+        CK(cudaStreamSynchronize(s.back));
     CK(cudaStreamSynchronize(c->stream));
     s.valid = false;
     s.early_rgb_done = nullptr;

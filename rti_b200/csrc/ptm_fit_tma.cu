@@ -144,14 +144,7 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
     float4 *m_s = reinterpret_cast<float4 *>(smem + Smem::matrix);
 
     const unsigned n = a.n_lights;
-    // In the fused encode this kernel is itself launched programmatically dependent on the previous
-    // K2 (its blocks become resident while K2's last blocks drain): nothing is read or written before
-    // that grid has completed.  A no-op for an ordinary launch.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (threadIdx.x == 0)
-        PTM_STAMP(0);
-    // a programmatically dependent K2 (the fused encode) may be scheduled as soon as SM resources free up
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
@@ -160,8 +153,21 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
         mbar_fence_init();
     }
     __syncthreads();
+    // In the fused encode this kernel is itself launched programmatically dependent on the previous
+    // K2 (its blocks become resident while K2's last blocks drain): nothing is read or written before
+    // that grid has completed.  A no-op for an ordinary launch.
+    // Exception: when the caller guarantees that the stack is not written by earlier work on the stream
+    // (a.stack_stable, ptmb_set_stack_stable), the PRODUCER warp starts its bulk copies right away -- the ring
+    // fills while the previous grid drains, which hides the 2-4 us ramp of the first stages.  The producer only
+    // reads the stack and draws tile numbers; it joins the dependency before it touches anything else (below).
+    const bool early_producer = a.stack_stable && warp == kConsumerWarps;
+    if (!early_producer)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0)
+        PTM_STAMP(0);
+    // a programmatically dependent K2 (the fused encode) may be scheduled as soon as SM resources free up
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned n_chunks = (n + L - 1) / L;
     Extrema ext;
     ext.init();
@@ -222,6 +228,8 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
             tile = next;
             slot ^= 1;
         }
+        if (early_producer)
+            asm volatile("griddepcontrol.wait;" ::: "memory");   // before the key hand-off below
     } else {
         // ----------------------------------------------------------- consumers
         const unsigned t = threadIdx.x;  // 0..255, owns pixels 4t..4t+3 of the tile

@@ -24,8 +24,14 @@ struct EncodeScratch {
     bool valid = false;
 };
 
+namespace ptm {
+struct HostState;   // ptm_hostpipe.h: staging pipe + stack mirror of the step-by-step host entries
+}
+
 struct ptmb_ctx {
     EncodeScratch enc;
+    ptm::HostState *host = nullptr;
+    int host_threads = 0;                    // staging threads of the host entries (0 = all hardware threads)
     // key hand-off between K1 and K2 of the fused device encode
     unsigned *ticket_dev = nullptr;          // last-block ticket counter (0 between launches)
     int *mailbox_dev = nullptr;              // local mailbox used when no peer exchange is attached
@@ -50,6 +56,7 @@ struct ptmb_ctx {
     int engine = 0;
     int relight_mode = 0;                    // PTMB_RELIGHT_*
     int fit_mode = 0;                        // PTMB_FIT_* flags of the LRGB-shaped entries
+    int stack_stable = 0;                    // ptmb_set_stack_stable
     int *keys_dev = nullptr;                 // scratch for the host-buffer entry points
     ptmb_scale_bias_t *sb_dev = nullptr;
     std::vector<float> light_host;

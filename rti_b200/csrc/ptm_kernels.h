@@ -64,6 +64,9 @@ struct FitArgs {
     // is the averaged YCbCr triplet), kFitRgbIn = the stack holds RGB triplets that are converted to YCbCr per
     // sample (libjpeg's integer formula) before anything else.  Both are served by the FFMA kernels.
     int mode;
+    // the caller guarantees that nothing queued earlier on the stream writes the stack: the ring kernel's
+    // producer may then start copying before the programmatic dependency on the previous grid has resolved
+    int stack_stable;
 };
 constexpr int kFitLum = 1;
 constexpr int kFitRgbIn = 2;

@@ -11,6 +11,7 @@
 // Each GPU has a persistent host thread that issues its work (cudaSetDevice is per thread, the
 // host-buffer path blocks on its copies, and at 8 GPUs a device-resident fit is 0.13 ms -- issuing
 // 8 x 2 launches from one thread would leave the GPUs waiting for the host).
+#include <algorithm>
 #include <condition_variable>
 #include <cstring>
 #include <functional>
@@ -25,6 +26,7 @@
 
 extern "C" int ptmb_internal_fail(const char *what, const char *detail);
 extern "C" int32_t *ptmb_internal_keys(ptmb_ctx_t *c);
+extern "C" void ptmb_internal_set_host_threads(ptmb_ctx_t *c, int n);
 extern "C" int ptmb_internal_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, size_t host_image_bytes,
                                              int sample_type, size_t width, size_t height, unsigned n_lights,
                                              const float *M, int format_planes, int32_t *keys_dev);
@@ -177,7 +179,13 @@ int ptmb_multi_create(const int *devices, int n_dev, ptmb_multi_t **out) {
             return 1;
         }
     }
-    // peer access between every pair; without it the keys travel through pinned host memory instead
+    // pageable host buffers are staged by host threads: share the cores between the GPUs
+    {
+        const int hw = (int) std::thread::hardware_concurrency();
+        for (int i = 0; i < n_dev; ++i)
+            ptmb_internal_set_host_threads(m->ctx[i], std::max(2, hw / n_dev));
+    }
+    // peer access between every pair
     bool peers = n_dev > 1;
     for (int i = 0; i < n_dev && peers; ++i)
         for (int j = 0; j < n_dev && peers; ++j) {

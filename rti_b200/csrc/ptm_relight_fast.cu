@@ -68,9 +68,9 @@ constexpr float kTwoM149 = 1.40129846e-45f;   // 2^-149, the smallest denormal: 
 
 // light table in shared memory: per direction six (l, l) pairs: u^2 v^2 uv u v, pad -- 48 bytes
 __device__ __forceinline__ void load_lights(float *light_s, const RelightArgs &a) {
-    for (unsigned i = threadIdx.x; i < a.n_dirs * 12; i += blockDim.x) {
+    for (unsigned i = threadIdx.x; i < (a.n_dirs + 1) * 12; i += blockDim.x) {   // + a spare entry for the look-ahead
         const unsigned d = i / 12, j = (i % 12) >> 1;
-        light_s[i] = j < 5 ? a.light[d * PTM_NCOEF + j] : 0.f;
+        light_s[i] = (j < 5 && d < a.n_dirs) ? a.light[d * PTM_NCOEF + j] : 0.f;
     }
     __syncthreads();
 }
@@ -107,7 +107,7 @@ __device__ __forceinline__ void store12(uint32_t *dst, const int (&z)[2][3][2]) 
 }
 
 // LRGB, 4 consecutive pixels of an output row per thread (width % 4 == 0).
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 relight_lrgb_fast_kernel(RelightArgs a) {
     extern __shared__ __align__(16) float light_s[];
     load_lights(light_s, a);
@@ -152,9 +152,12 @@ relight_lrgb_fast_kernel(RelightArgs a) {
         }
         uint32_t *dst = reinterpret_cast<uint32_t *>(a.out + g * 12);
         const size_t dir_words = pixels * 3 / 4;
+        // The light table comes from shared memory ~30 cycles after it is asked for: the pairs of direction d + 1
+        // are requested before direction d is evaluated (the table has one spare entry, so no bounds test).
+        LightPairs l = light_pairs(light_s, 0);
 #pragma unroll 2
         for (unsigned d = 0; d < a.n_dirs; ++d) {
-            const LightPairs l = light_pairs(light_s, d);
+            const LightPairs nxt = light_pairs(light_s, d + 1);
             int z[2][3][2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -165,6 +168,7 @@ relight_lrgb_fast_kernel(RelightArgs a) {
             }
             store12(dst, z);
             dst += dir_words;
+            l = nxt;
         }
     }
 }
@@ -207,9 +211,9 @@ relight_rgb_fast_kernel(RelightArgs a) {
         }
         uint32_t *dst = reinterpret_cast<uint32_t *>(a.out + g * 12);
         const size_t dir_words = pixels * 3 / 4;
-#pragma unroll 2
+        LightPairs l = light_pairs(light_s, 0);
         for (unsigned d = 0; d < a.n_dirs; ++d) {
-            const LightPairs l = light_pairs(light_s, d);
+            const LightPairs nxt = light_pairs(light_s, d + 1);   // requested one direction ahead (spare table entry)
             int z[2][3][2];
 #pragma unroll
             for (int h = 0; h < 2; ++h)
@@ -218,6 +222,7 @@ relight_rgb_fast_kernel(RelightArgs a) {
                     unpk_bits(mul2_rz(poly2(A[ch][h], l), kDen), z[h][ch][0], z[h][ch][1]);
             store12(dst, z);
             dst += dir_words;
+            l = nxt;
         }
     }
 }
@@ -240,7 +245,7 @@ cudaError_t launch_relight_fast(const RelightArgs &a, bool lrgb, int sm_count, c
     if (!ok)
         return cudaErrorNotSupported;
     const size_t want = (pixels / 4 + kThreads - 1) / kThreads;
-    const size_t smem = (size_t) a.n_dirs * 12 * sizeof(float);
+    const size_t smem = ((size_t) a.n_dirs + 1) * 12 * sizeof(float);
     if (lrgb) {
         const size_t cap = (size_t) sm_count * 8;
         relight_lrgb_fast_kernel<<<(unsigned) (want < cap ? want : cap), kThreads, smem, st>>>(a);

