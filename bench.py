@@ -476,6 +476,10 @@ def run_b200(args):
                      exchange=os.environ.get("PTM_EXCHANGE", "p2p"))
     enc.ctx.synth(SEED, 0, U8, r0 * W, P, light_q14(L), stack, P * 3)
     torch.cuda.synchronize()
+    # the stack is resident and complete before the first encode is enqueued: K1's copy warp may start while the
+    # previous K2 drains (ptmb_set_stack_stable; PTM_STACK_STABLE=0 measures without it)
+    stack_stable = os.environ.get("PTM_STACK_STABLE", "1") == "1"
+    enc.ctx.set_stack_stable(stack_stable)
 
     def barrier():
         if world > 1:
@@ -610,6 +614,7 @@ def run_b200(args):
                    "rows_per_gpu": rows, "l2": "inputs larger than L2 (%.0f MB stack per GPU, streamed once per step)"
                                                % (stack.numel() / 1e6),
                    "driver": "one process per GPU (torchrun)" if world > 1 else "one process",
+                   "stack_stable": stack_stable,
                    "exchange": {"none": "none", "nccl": "int32 MAX all-reduce of 12 keys (NCCL)",
                                 "p2p": "12 int32 keys written into every peer's mailbox over NVLink by K1's last block, picked up in K2's prologue"}
                                [enc.exchange_kind]},

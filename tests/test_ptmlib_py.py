@@ -119,7 +119,6 @@ def test_pinned_and_pageable_buffers_agree(oracle, dome1):
     f1 = P.ptm_fit_poly_jsample(info, stack, 3, M)
     f2 = P.ptm_fit_poly_jsample(info, pinned.numpy(), 3, M)
     np.testing.assert_array_equal(f1, f2)
-    np.testing.assert_array_equal(f1.reshape(H, W, 6), a["coeffs"][0].reshape(H, W, 6) * 0 + f1.reshape(H, W, 6))
     rows = [0, 299, 599]
     np.testing.assert_allclose(f1.reshape(H, W, 6)[rows], oracle.fit_u8(np.ascontiguousarray(stack[:, rows]), M),
                                rtol=0, atol=2e-3)
