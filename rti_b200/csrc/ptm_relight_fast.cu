@@ -30,6 +30,7 @@ namespace ptm {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kDefaultVariant = 1;
 
 typedef unsigned long long f32x2;
 
@@ -100,21 +101,53 @@ __device__ __forceinline__ f32x2 poly2(const f32x2 *c, const LightPairs &l) {
 }
 
 // bytes p0r p0g p0b p1r | p1g p1b p2r p2g | p2b p3r p3g p3b from z[pair][channel][pixel of the pair]
-__device__ __forceinline__ void store12(uint32_t *dst, const int (&z)[2][3][2]) {
-    __stcs(dst + 0, bytes4(z[0][0][0], z[0][1][0], z[0][2][0], z[0][0][1]));
-    __stcs(dst + 1, bytes4(z[0][1][1], z[0][2][1], z[1][0][0], z[1][1][0]));
-    __stcs(dst + 2, bytes4(z[1][2][0], z[1][0][1], z[1][1][1], z[1][2][1]));
+__device__ __forceinline__ void words12(const int (&z)[2][3][2], unsigned (&w)[3]) {
+    w[0] = bytes4(z[0][0][0], z[0][1][0], z[0][2][0], z[0][0][1]);
+    w[1] = bytes4(z[0][1][1], z[0][2][1], z[1][0][0], z[1][1][0]);
+    w[2] = bytes4(z[1][2][0], z[1][0][1], z[1][1][1], z[1][2][1]);
 }
 
-// LRGB, 4 consecutive pixels of an output row per thread (width % 4 == 0).
+// A lane's 12 output bytes of one direction leave the SM in one of two ways:
+//   narrow  three 4-byte stores per lane.  A warp instruction then touches twelve 32-byte sectors with 8-12 bytes
+//           each: every sector of the raster is written by three separate partial stores that L2 has to merge.
+//   wide    the warp's 384 contiguous bytes are transposed through 384 bytes of shared memory (three conflict-free
+//           4-byte stores per lane, one 16-byte load by lanes 0..23) and leave as ONE 16-byte store per lane:
+//           whole sectors, a third of the L2 write transactions.  Double buffered by direction parity, so one
+//           __syncwarp per direction orders the shared-memory accesses.
+template <bool kWide>
+__device__ __forceinline__ void store_dir(const unsigned (&w)[3], uint32_t *dst_lane, uint4 *dst_warp, uint32_t *stage,
+                                          unsigned lane, unsigned d) {
+    if (!kWide) {
+        __stcs(dst_lane + 0, w[0]);
+        __stcs(dst_lane + 1, w[1]);
+        __stcs(dst_lane + 2, w[2]);
+        return;
+    }
+    uint32_t *buf = stage + (d & 1u) * 96u;
+    buf[3 * lane + 0] = w[0];
+    buf[3 * lane + 1] = w[1];
+    buf[3 * lane + 2] = w[2];
+    __syncwarp();
+    if (lane < 24)
+        __stcs(dst_warp + lane, reinterpret_cast<const uint4 *>(buf)[lane]);
+}
+
+constexpr unsigned kWarpsPerBlock = kThreads / 32;
+constexpr size_t kStageBytes = (size_t) kWarpsPerBlock * 2 * 96 * sizeof(uint32_t);   // 6 KB per block
+
+// LRGB, 4 consecutive pixels of an output row per thread (width % 4 == 0); a warp owns 128 consecutive pixels.
+template <bool kWide, bool kPrefetch>
 __global__ void __launch_bounds__(kThreads, 3)
 relight_lrgb_fast_kernel(RelightArgs a) {
-    extern __shared__ __align__(16) float light_s[];
+    extern __shared__ __align__(16) float smem_f[];
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smem_f) + (threadIdx.x >> 5) * 192;
+    float *light_s = smem_f + kStageBytes / sizeof(float);
     load_lights(light_s, a);
 
     const size_t pixels = a.width * a.height;
     const size_t groups = pixels / 4;
     const size_t gw = a.width / 4;
+    const unsigned lane = threadIdx.x & 31;
     float sc[PTM_NCOEF], kb[PTM_NCOEF];
 #pragma unroll
     for (int k = 0; k < PTM_NCOEF; ++k) {
@@ -122,9 +155,14 @@ relight_lrgb_fast_kernel(RelightArgs a) {
         sc[k] = (a.scale[k] * 0.003921568627450980392f) * kTwoM74;
         kb[k] = 8388608.0f + (float) a.bias[k];
     }
-    for (size_t g = (size_t) blockIdx.x * blockDim.x + threadIdx.x; g < groups;
-         g += (size_t) gridDim.x * blockDim.x) {
-        const size_t y = g / gw, xg = g - y * gw;
+    // warp-uniform loop: gb = the warp's first group; lanes past the end of the image idle
+    for (size_t gb = (size_t) blockIdx.x * blockDim.x + (threadIdx.x & ~31u); gb < groups;
+         gb += (size_t) gridDim.x * blockDim.x) {
+        const size_t g = gb + lane;
+        const bool live = g < groups;
+        const bool whole_warp = gb + 32 <= groups;
+        const size_t gs = live ? g : groups - 1;
+        const size_t y = gs / gw, xg = gs - y * gw;
         const size_t p = (a.height - 1 - y) * a.width + xg * 4;   // stored row height-1-y (:587-589)
         const uint2 *c2 = reinterpret_cast<const uint2 *>(a.plane[0] + p * PTM_NCOEF);
         const uint32_t *r32 = reinterpret_cast<const uint32_t *>(a.plane[1] + p * 3);
@@ -150,14 +188,19 @@ relight_lrgb_fast_kernel(RelightArgs a) {
             for (int ch = 0; ch < 3; ++ch)
                 C[h][ch] = pk(col[2 * h][ch], col[2 * h + 1][ch]);
         }
-        uint32_t *dst = reinterpret_cast<uint32_t *>(a.out + g * 12);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(a.out + gs * 12);
+        uint4 *dst_warp = reinterpret_cast<uint4 *>(a.out + gb * 12);
         const size_t dir_words = pixels * 3 / 4;
-        // The light table comes from shared memory ~30 cycles after it is asked for: the pairs of direction d + 1
-        // are requested before direction d is evaluated (the table has one spare entry, so no bounds test).
+        // kPrefetch: the light pairs of direction d + 1 are requested from shared memory before direction d is
+        // evaluated (the table has a spare entry, so no bounds test)
         LightPairs l = light_pairs(light_s, 0);
 #pragma unroll 2
         for (unsigned d = 0; d < a.n_dirs; ++d) {
-            const LightPairs nxt = light_pairs(light_s, d + 1);
+            LightPairs nxt;
+            if (kPrefetch)
+                nxt = light_pairs(light_s, d + 1);
+            else
+                l = light_pairs(light_s, d);
             int z[2][3][2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -166,30 +209,47 @@ relight_lrgb_fast_kernel(RelightArgs a) {
                 for (int ch = 0; ch < 3; ++ch)
                     unpk_bits(mul2_rz(L, C[h][ch]), z[h][ch][0], z[h][ch][1]);   // (L 2^-74)(c 2^-75): bits = floor(L c)
             }
-            store12(dst, z);
+            unsigned w[3];
+            words12(z, w);
+            if (kWide && whole_warp)
+                store_dir<true>(w, dst, dst_warp, stage, lane, d);
+            else if (live)
+                store_dir<false>(w, dst, dst_warp, stage, lane, d);
             dst += dir_words;
-            l = nxt;
+            dst_warp += dir_words / 4;
+            if (kPrefetch)
+                l = nxt;
         }
+        if (kWide)
+            __syncwarp();   // the next pixel group's first direction reuses buffer 0
     }
 }
 
 // RGB formats, 4 consecutive pixels per thread: CLIP(POLY) per channel (rti-builder/ptmlib.c:610-619).
+template <bool kWide, bool kPrefetch>
 __global__ void __launch_bounds__(kThreads, 2)
 relight_rgb_fast_kernel(RelightArgs a) {
-    extern __shared__ __align__(16) float light_s[];
+    extern __shared__ __align__(16) float smem_f[];
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smem_f) + (threadIdx.x >> 5) * 192;
+    float *light_s = smem_f + kStageBytes / sizeof(float);
     load_lights(light_s, a);
 
     const size_t pixels = a.width * a.height;
     const size_t groups = pixels / 4;
     const size_t gw = a.width / 4;
+    const unsigned lane = threadIdx.x & 31;
     const f32x2 kDen = pk(kTwoM149, kTwoM149);
     float kb[PTM_NCOEF];
 #pragma unroll
     for (int k = 0; k < PTM_NCOEF; ++k)
         kb[k] = 8388608.0f + (float) a.bias[k];
-    for (size_t g = (size_t) blockIdx.x * blockDim.x + threadIdx.x; g < groups;
-         g += (size_t) gridDim.x * blockDim.x) {
-        const size_t y = g / gw, xg = g - y * gw;
+    for (size_t gb = (size_t) blockIdx.x * blockDim.x + (threadIdx.x & ~31u); gb < groups;
+         gb += (size_t) gridDim.x * blockDim.x) {
+        const size_t g = gb + lane;
+        const bool live = g < groups;
+        const bool whole_warp = gb + 32 <= groups;
+        const size_t gs = live ? g : groups - 1;
+        const size_t y = gs / gw, xg = gs - y * gw;
         const size_t p = (a.height - 1 - y) * a.width + xg * 4;
         f32x2 A[3][2][PTM_NCOEF];
 #pragma unroll
@@ -209,21 +269,35 @@ relight_rgb_fast_kernel(RelightArgs a) {
                 for (int k = 0; k < PTM_NCOEF; ++k)
                     A[ch][h][k] = pk(u[2 * h][k], u[2 * h + 1][k]);
         }
-        uint32_t *dst = reinterpret_cast<uint32_t *>(a.out + g * 12);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(a.out + gs * 12);
+        uint4 *dst_warp = reinterpret_cast<uint4 *>(a.out + gb * 12);
         const size_t dir_words = pixels * 3 / 4;
         LightPairs l = light_pairs(light_s, 0);
         for (unsigned d = 0; d < a.n_dirs; ++d) {
-            const LightPairs nxt = light_pairs(light_s, d + 1);   // requested one direction ahead (spare table entry)
+            LightPairs nxt;
+            if (kPrefetch)
+                nxt = light_pairs(light_s, d + 1);   // requested one direction ahead (spare table entry)
+            else
+                l = light_pairs(light_s, d);
             int z[2][3][2];
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch)
                     unpk_bits(mul2_rz(poly2(A[ch][h], l), kDen), z[h][ch][0], z[h][ch][1]);
-            store12(dst, z);
+            unsigned w[3];
+            words12(z, w);
+            if (kWide && whole_warp)
+                store_dir<true>(w, dst, dst_warp, stage, lane, d);
+            else if (live)
+                store_dir<false>(w, dst, dst_warp, stage, lane, d);
             dst += dir_words;
-            l = nxt;
+            dst_warp += dir_words / 4;
+            if (kPrefetch)
+                l = nxt;
         }
+        if (kWide)
+            __syncwarp();
     }
 }
 
@@ -245,13 +319,34 @@ cudaError_t launch_relight_fast(const RelightArgs &a, bool lrgb, int sm_count, c
     if (!ok)
         return cudaErrorNotSupported;
     const size_t want = (pixels / 4 + kThreads - 1) / kThreads;
-    const size_t smem = ((size_t) a.n_dirs + 1) * 12 * sizeof(float);
+    const size_t smem = kStageBytes + ((size_t) a.n_dirs + 1) * 12 * sizeof(float);
+    // tuning aid (result-equivalent kernel shapes): bit 0 = 16-byte stores through a shared-memory transpose,
+    // bit 1 = light table look-ahead.  The default is what measured fastest.
+    static int variant = -1;
+    if (variant < 0) {
+        const char *v = getenv("PTM_RELIGHT_VARIANT");
+        variant = v ? atoi(v) & 3 : kDefaultVariant;
+    }
+    const bool wide = (variant & 1) && ((uintptr_t) a.out % 16 == 0) && (pixels * 3) % 16 == 0;
+    const int vsel = (wide ? 1 : 0) | (variant & 2);
     if (lrgb) {
         const size_t cap = (size_t) sm_count * 8;
-        relight_lrgb_fast_kernel<<<(unsigned) (want < cap ? want : cap), kThreads, smem, st>>>(a);
+        const unsigned grid = (unsigned) (want < cap ? want : cap);
+        switch (vsel) {
+        case 0: relight_lrgb_fast_kernel<false, false><<<grid, kThreads, smem, st>>>(a); break;
+        case 1: relight_lrgb_fast_kernel<true, false><<<grid, kThreads, smem, st>>>(a); break;
+        case 2: relight_lrgb_fast_kernel<false, true><<<grid, kThreads, smem, st>>>(a); break;
+        default: relight_lrgb_fast_kernel<true, true><<<grid, kThreads, smem, st>>>(a); break;
+        }
     } else {
         const size_t cap = (size_t) sm_count * 2;
-        relight_rgb_fast_kernel<<<(unsigned) (want < cap ? want : cap), kThreads, smem, st>>>(a);
+        const unsigned grid = (unsigned) (want < cap ? want : cap);
+        switch (vsel) {
+        case 0: relight_rgb_fast_kernel<false, false><<<grid, kThreads, smem, st>>>(a); break;
+        case 1: relight_rgb_fast_kernel<true, false><<<grid, kThreads, smem, st>>>(a); break;
+        case 2: relight_rgb_fast_kernel<false, true><<<grid, kThreads, smem, st>>>(a); break;
+        default: relight_rgb_fast_kernel<true, true><<<grid, kThreads, smem, st>>>(a); break;
+        }
     }
     return cudaGetLastError();
 }

@@ -247,3 +247,61 @@ def test_reference_mains_linked_against_our_library(oracle, dome1, tmp_path, fmt
         assert ra.returncode == 0 and rb.returncode == 0
         for f in sorted(os.listdir(os.path.join(d, "b")))[::7]:
             assert open(os.path.join(d, "a", f), "rb").read() == open(os.path.join(d, "b", f), "rb").read(), f
+
+
+def test_jpeg_ptm_plane_prediction_and_side_info(oracle, tmp_path):
+    """A PTM_FORMAT_JPEG_LRGB file that uses everything the reference's reader supports beyond what its writer
+    emits (rti-builder/ptmlib.c:249-284,421-440): a non-identity plane order, planes predicted from other planes
+    (reference_planes >= 0), one of them from the INVERTED reference (transforms bit 0), and side-info patches
+    (5-byte records, one with an out-of-range offset that must be ignored).  Decoded by libptm.so's reader and by
+    the reference's unmodified decoder: the relit rasters are byte-identical, and equal the oracle's relight of
+    the planes reconstructed independently here."""
+    import struct
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(11)
+    W, H, n = 24, 16, 9
+    P = W * H
+    stored = rng.integers(0, 256, (n, P), dtype=np.uint8)            # what the streams hold
+    order = [3, 0, 1, 2, 5, 4, 8, 6, 7]                              # processing rank of each component
+    ref_planes = [-1, 0, -1, -1, 1, -1, -1, 6, -1]                   # 1 <- 0, 4 <- 1 (inverted), 7 <- 6
+    transforms = [0, 0, 0, 0, 1, 0, 0, 0, 0]
+    side = {2: [(5, 200), (P - 1, 7), (P + 40, 99)], 4: [(0, 1), (17, 255)]}
+    side_bytes = {i: b"".join(struct.pack(">IB", off, val) for off, val in recs) for i, recs in side.items()}
+    # independent reconstruction, in processing order (rti-builder/ptmlib.c:421-440)
+    planes = stored.copy()
+    for rank in range(n):
+        comp = order.index(rank)
+        r = ref_planes[comp]
+        if r > -1:
+            src = planes[r].astype(np.int32)
+            if transforms[comp] & 1:
+                src = 255 - src
+            planes[comp] = (planes[comp].astype(np.int32) + src - 128).astype(np.uint8)   # JSAMPLE wrap-around
+        for off, val in side.get(comp, []):
+            if off < P:
+                planes[comp][off] = val
+    coef = np.stack([planes[k] for k in range(6)], -1).reshape(H, W, 6)
+    rgb = np.stack([planes[6 + k] for k in range(3)], -1).reshape(H, W, 3)
+    scale = np.array([0.9, 1.1, 0.7, 1.3, 0.8, 1.0], np.float32)
+    bias = np.array([120, 131, 117, 125, 140, 10], np.int32)
+    streams = [b"RAWJ" + struct.pack("<III", W, H, 1) + stored[i].tobytes() for i in range(n)]
+
+    def ints(v):
+        return (" ".join(str(int(x)) for x in v) + "\n").encode()
+
+    blob = b"PTM_1.2\nPTM_FORMAT_JPEG_LRGB\n%d\n%d\n" % (W, H)
+    blob += (" ".join("%f" % s for s in scale) + "\n").encode() + ints(bias)
+    blob += ints([90]) + ints(transforms) + ints([0] * n) + ints([0] * n) + ints(order) + ints(ref_planes)
+    blob += ints([len(s) for s in streams]) + ints([len(side_bytes.get(i, b"")) for i in range(n)])
+    for i in range(n):
+        blob += streams[i] + side_bytes.get(i, b"")
+    path = os.path.join(str(tmp_path), "predicted.ptm")
+    open(path, "wb").write(blob)
+    for uv in (("0.25", "-0.5"), ("0", "0")):
+        ra = run([os.path.join(BIN, "ptm-decoder"), path, *uv])
+        rb = run([os.path.join(REF, "ptm-decoder-ref"), path, *uv])
+        assert ra.returncode == 0 and rb.returncode == 0, ra.stderr.decode() + rb.stderr.decode()
+        assert ra.stdout == rb.stdout, "libptm.so and the reference decoder disagree on a predicted / patched PTM"
+        want = oracle.relight_lrgb(coef, rgb, oracle.header_roundtrip(scale), bias, float(uv[0]), float(uv[1]))
+        np.testing.assert_array_equal(oracle.read_rawj(ra.stdout), want)
