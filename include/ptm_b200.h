@@ -302,6 +302,14 @@ int ptmb_multi_encode_lrgb_dev (ptmb_multi_t *multi, const void *const *stack_de
                                 uint8_t *const *rgb_dev, uint8_t *const *coef_bytes_dev,
                                 ptmb_scale_bias_t *const *sb_dev);
 
+/* The same for the RGB formats: coeffs_dev float [3][pixels][6] and coef_bytes_dev uint8 [3][pixels][6], planes
+ * contiguous; the tensor-core fit kernel hands the keys over, ONE K2 launch quantises the three planes.  Falls back
+ * to separate launches when the tensor-core engine does not take the layout.
+ * Call sequence replaced: rti-builder/ptm-encoder.c:272-284,406. */
+int ptmb_encode_rgb_dev (ptmb_ctx_t *ctx, ptmb_xchg_t *xchg, const void *stack_dev, int sample_type,
+                         size_t image_stride, size_t pixels, float *coeffs_dev, uint8_t *coef_bytes_dev,
+                         ptmb_scale_bias_t *sb_dev);
+
 /* A promise by the caller about the stacks it passes to ptmb_encode_lrgb_dev: nothing queued earlier on the
  * context's stream writes them (they were complete before the PREVIOUS call on the stream was enqueued -- e.g. a
  * resident stack encoded repeatedly, or slabs uploaded on another stream and joined by an event earlier on).

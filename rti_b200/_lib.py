@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libptm_b200.so")
+LIB_PATH = os.environ.get("PTM_B200_LIB") or os.path.join(HERE, "lib", "libptm_b200.so")   # override: tuning builds only
 
 NCOEF = 6
 NKEYS = 12
@@ -88,6 +88,7 @@ _SIGNATURES = {
     "ptmb_multi_synchronize": ([_vp], _int),
     "ptmb_multi_encode_host": ([_vp, _vp, _int, _sz, _sz, C.c_uint, _vp, _int, C.POINTER(_vp), _vp, _vp], _int),
     "ptmb_multi_encode_lrgb_dev": ([_vp, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp], _int),
+    "ptmb_encode_rgb_dev": ([_vp, _vp, _vp, _int, _sz, _sz, _vp, _vp, _vp], _int),
     "ptmb_probe_arm": ([_vp, C.c_uint], _int),
     "ptmb_probe_read": ([_vp, _vp, C.c_uint, C.POINTER(C.c_uint)], _int),
     "ptmb_jpeg_info": ([_vp, _vp, _sz, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)], _int),

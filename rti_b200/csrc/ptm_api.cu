@@ -455,6 +455,61 @@ int ptmb_encode_lrgb_dev(ptmb_ctx_t *c, ptmb_xchg_t *x, const void *stack_dev, i
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// The same for the RGB formats (three coefficient planes, rti-builder/ptm-encoder.c:272-284,406): the
+// tensor-core fit kernel carries the key hand-off, one K2 launch covers the three contiguous planes.
+// ---------------------------------------------------------------------------
+int ptmb_encode_rgb_dev(ptmb_ctx_t *c, ptmb_xchg_t *x, const void *stack_dev, int sample_type, size_t image_stride,
+                        size_t pixels, float *coeffs_dev, uint8_t *coef_bytes_dev, ptmb_scale_bias_t *sb_dev) {
+    ptm::FitArgs a;
+    if (make_fit_args(c, stack_dev, image_stride, pixels, a))
+        return 1;
+    REQUIRE(sample_type == PTMB_U8 || sample_type == PTMB_U16, "RGB fit takes uint8 or uint16 stacks");
+    REQUIRE(coeffs_dev && coef_bytes_dev, "output pointer is NULL");
+    REQUIRE(image_stride >= pixels * 3 * sample_size(sample_type), "image_stride smaller than one image");
+    REQUIRE(!x || x->device == c->device, "exchange belongs to another device");
+    CK(cudaSetDevice(c->device));
+    a.coeffs = coeffs_dev;
+    a.plane_stride = pixels * PTMB_COEFFICIENTS;   // contiguous planes: one K2 launch covers all three
+    a.keys = c->keys_dev;
+    ptm::KeySource src{};
+    size_t done = 0;
+    const int fmt_default = sample_type == PTMB_U8 ? ptm::kDefaultEngineRgbU8 : ptm::kDefaultEngineRgbU16;
+    const unsigned unit_px = sample_type == PTMB_U8 ? 128 : 64;
+    if (pixels > 0 && ptm::resolve_engine(a.engine, fmt_default) == 2 && (pixels % unit_px) % 16 == 0) {
+        a.handoff.ticket = c->ticket_dev;
+        a.handoff.tile_counter = a.tile_counter;
+        a.handoff.world = x ? x->world : 1;
+        a.handoff.rank = x ? x->rank : 0;
+        a.handoff.epoch = x ? x->epoch + 1 : c->epoch + 1;
+        for (int r = 0; r < a.handoff.world; ++r)
+            a.handoff.mailbox[r] = x ? x->mailbox[r] : c->mailbox_dev;
+        CK(ptm::launch_fit_mma(a, sample_type == PTMB_U8 ? 0 : 2, c->sm_count, c->stream, &done));
+        if (done == pixels) {
+            if (x)
+                ++x->epoch;
+            else
+                ++c->epoch;
+            src.mailbox = x ? x->local : c->mailbox_dev;
+            src.world = a.handoff.world;
+            src.epoch = a.handoff.epoch;
+        } else {
+            REQUIRE(done == 0, "internal: partial tensor-core launch with a hand-off");
+        }
+    }
+    if (!src.mailbox) {
+        a.handoff = ptm::KeyHandoff{};
+        CK(ptm::launch_fit_rgb(a, sample_type, c->sm_count, c->stream));
+        if (x && ptmb_xchg_allreduce_max(c, x, c->keys_dev))
+            return 1;
+        src.keys = c->keys_dev;
+    }
+    CK(ptm::launch_quantise(coeffs_dev, pixels * 3, src, coef_bytes_dev, sb_dev, false, c->sm_count, c->stream));
+    if (!src.mailbox)
+        CK(ptm::launch_keys_init(c->keys_dev, c->stream));
+    return 0;
+}
+
 // Timing probes: the next `pairs` calls of ptmb_encode_lrgb_dev record a CUDA event before and after
 // their fit stage on the context's stream; ptmb_probe_read returns the elapsed milliseconds.
 int ptmb_probe_arm(ptmb_ctx_t *c, unsigned pairs) {

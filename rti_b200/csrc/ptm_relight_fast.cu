@@ -136,7 +136,9 @@ constexpr unsigned kWarpsPerBlock = kThreads / 32;
 constexpr size_t kStageBytes = (size_t) kWarpsPerBlock * 2 * 96 * sizeof(uint32_t);   // 6 KB per block
 
 // LRGB, 4 consecutive pixels of an output row per thread (width % 4 == 0); a warp owns 128 consecutive pixels.
-template <bool kWide, bool kPrefetch>
+// kDebug (only instantiated in -DPTM_TUNING builds, results are NOT produced): 1 = arithmetic without the stores,
+// 2 = the stores without the arithmetic, 3 = as 2 with default-policy stores instead of streaming ones.
+template <bool kWide, bool kPrefetch, int kDebug = 0>
 __global__ void __launch_bounds__(kThreads, 3)
 relight_lrgb_fast_kernel(RelightArgs a) {
     extern __shared__ __align__(16) float smem_f[];
@@ -148,6 +150,8 @@ relight_lrgb_fast_kernel(RelightArgs a) {
     const size_t groups = pixels / 4;
     const size_t gw = a.width / 4;
     const unsigned lane = threadIdx.x & 31;
+    unsigned dbg = 0;
+    (void) dbg;
     float sc[PTM_NCOEF], kb[PTM_NCOEF];
 #pragma unroll
     for (int k = 0; k < PTM_NCOEF; ++k) {
@@ -201,20 +205,35 @@ relight_lrgb_fast_kernel(RelightArgs a) {
                 nxt = light_pairs(light_s, d + 1);
             else
                 l = light_pairs(light_s, d);
-            int z[2][3][2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const f32x2 L = poly2(A[h], l);
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch)
-                    unpk_bits(mul2_rz(L, C[h][ch]), z[h][ch][0], z[h][ch][1]);   // (L 2^-74)(c 2^-75): bits = floor(L c)
-            }
             unsigned w[3];
-            words12(z, w);
-            if (kWide && whole_warp)
+            if (kDebug >= 2) {
+                w[0] = d + lane;
+                w[1] = d * 3 + lane;
+                w[2] = d ^ lane;
+            } else {
+                int z[2][3][2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const f32x2 L = poly2(A[h], l);
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch)
+                        unpk_bits(mul2_rz(L, C[h][ch]), z[h][ch][0], z[h][ch][1]);   // (L 2^-74)(c 2^-75): bits = floor(L c)
+                }
+                words12(z, w);
+            }
+            if (kDebug == 1) {
+                dbg ^= w[0] + w[1] + w[2];
+            } else if (kDebug == 3) {
+                if (live) {
+                    dst[0] = w[0];
+                    dst[1] = w[1];
+                    dst[2] = w[2];
+                }
+            } else if (kWide && whole_warp) {
                 store_dir<true>(w, dst, dst_warp, stage, lane, d);
-            else if (live)
+            } else if (live) {
                 store_dir<false>(w, dst, dst_warp, stage, lane, d);
+            }
             dst += dir_words;
             dst_warp += dir_words / 4;
             if (kPrefetch)
@@ -223,6 +242,8 @@ relight_lrgb_fast_kernel(RelightArgs a) {
         if (kWide)
             __syncwarp();   // the next pixel group's first direction reuses buffer 0
     }
+    if (kDebug == 1 && dbg == 0x12345678u)
+        a.out[0] = 1;
 }
 
 // RGB formats, 4 consecutive pixels per thread: CLIP(POLY) per channel (rti-builder/ptmlib.c:610-619).
@@ -332,6 +353,17 @@ cudaError_t launch_relight_fast(const RelightArgs &a, bool lrgb, int sm_count, c
     if (lrgb) {
         const size_t cap = (size_t) sm_count * 8;
         const unsigned grid = (unsigned) (want < cap ? want : cap);
+#ifdef PTM_TUNING
+        static int debug = -1;
+        if (debug < 0) {
+            const char *v = getenv("PTM_RELIGHT_DEBUG");
+            debug = v ? atoi(v) : 0;
+        }
+        if (debug == 1) { relight_lrgb_fast_kernel<false, false, 1><<<grid, kThreads, smem, st>>>(a); return cudaGetLastError(); }
+        if (debug == 2) { relight_lrgb_fast_kernel<false, false, 2><<<grid, kThreads, smem, st>>>(a); return cudaGetLastError(); }
+        if (debug == 3) { relight_lrgb_fast_kernel<false, false, 3><<<grid, kThreads, smem, st>>>(a); return cudaGetLastError(); }
+        if (debug == 4) { relight_lrgb_fast_kernel<true, false, 2><<<grid, kThreads, smem, st>>>(a); return cudaGetLastError(); }
+#endif
         switch (vsel) {
         case 0: relight_lrgb_fast_kernel<false, false><<<grid, kThreads, smem, st>>>(a); break;
         case 1: relight_lrgb_fast_kernel<true, false><<<grid, kThreads, smem, st>>>(a); break;

@@ -147,6 +147,14 @@ class Context:
                                                   sample_type, image_stride, pixels, _ptr(coeffs), _ptr(rgb),
                                                   _ptr(coef_bytes), _ptr(scale_bias)))
 
+    def encode_rgb_dev(self, stack, image_stride, pixels, coeffs, coef_bytes, scale_bias=None, xchg=None,
+                       sample_type=U8):
+        """Whole device-resident RGB-format encode of one slab (tensor-core K1 -> key hand-off -> one K2 over the
+        three contiguous planes)."""
+        _lib.check(self._lib.ptmb_encode_rgb_dev(self._h, None if xchg is None else xchg._h, _ptr(stack), sample_type,
+                                                 image_stride, pixels, _ptr(coeffs), _ptr(coef_bytes),
+                                                 _ptr(scale_bias)))
+
     def probe_arm(self, pairs):
         _lib.check(self._lib.ptmb_probe_arm(self._h, pairs))
 

@@ -149,6 +149,13 @@ class PtmEncoder:
             self.ctx.encode_lrgb_dev(stack, self.pixels * 3 * stack.element_size(), self.pixels, self.coeffs,
                                      self.rgb, self.coef_bytes, self.sb, xchg=self.xchg, sample_type=st)
             return
+        if self.planes == 3 and self.exchange_kind in ("none", "p2p") and self.keep_coeffs and stack.is_contiguous():
+            # RGB formats: tensor-core K1 with the key hand-off + one K2 over the three planes (two launches)
+            self._use_current_stream()
+            st = {torch.uint8: U8, torch.uint16: U16}[stack.dtype]
+            self.ctx.encode_rgb_dev(stack, self.pixels * 3 * stack.element_size(), self.pixels, self.coeffs,
+                                    self.coef_bytes, self.sb, xchg=self.xchg, sample_type=st)
+            return
         self.fit(stack)
         self.exchange()
         self.quantise()

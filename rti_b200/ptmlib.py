@@ -192,24 +192,44 @@ def ptm_normal(coeffs):
     return tuple(x.value for x in o)
 
 
-def encode_lrgb_stepwise(stack, M):
+def stepwise_buffers(width, height):
+    """The caller-owned host buffers of the step-by-step sequence (what the reference's main allocates,
+    rti-builder/ptm-encoder.c:270,307): float coefficients + the two LRGB blocks, already touched."""
+    header = ptm_alloc_header("PTM_FORMAT_LRGB", width, height)
+    blocks = ptm_alloc_blocks(header)
+    coeffs = np.zeros((width * height, PTM_COEFFICIENTS), np.float32)
+    for b in blocks:
+        b.fill(0)
+    return dict(coeffs=coeffs, blocks=blocks)
+
+
+def encode_lrgb_stepwise(stack, M, buffers=None):
     """The reference encoder's LRGB call sequence, step by step, on HOST (pageable) numpy buffers
     (rti-builder/ptm-encoder.c:313-353,406):
 
         ptm_fit_poly_jsample -> ptm_cbcr_avg -> colour + normalise loop (ptm_lrgb_finish) -> ptm_scale_coefficients
 
-    stack: uint8 [n][H][W][3] (YCbCr, stored row order).  Returns dict(coef, rgb, scale, bias, coeffs)."""
+    stack: uint8 [n][H][W][3] (YCbCr, stored row order).  `buffers` (stepwise_buffers) are reused if given.
+    Returns dict(coef, rgb, scale, bias, coeffs)."""
     assert stack.dtype == np.uint8 and stack.ndim == 4 and stack.shape[3] == 3 and stack.flags.c_contiguous
     n, H, W, _ = stack.shape
     info = image_info(W, H, n)
     header = ptm_alloc_header("PTM_FORMAT_LRGB", W, H)
-    blocks = ptm_alloc_blocks(header)
+    buffers = buffers or stepwise_buffers(W, H)
+    blocks, coeffs = buffers["blocks"], buffers["coeffs"]
     M = np.ascontiguousarray(M, dtype=np.float32)
-    coeffs = np.empty((info.pixels, PTM_COEFFICIENTS), np.float32)
+    import time
     L = lib()
+    t = [time.perf_counter()]
     L.ptm_fit_poly_jsample(C.byref(info), stack.ctypes.data, 3, M.ctypes.data, coeffs.ctypes.data)
+    t.append(time.perf_counter())
     L.ptm_cbcr_avg(C.byref(info), stack.ctypes.data, blocks[1].ctypes.data)
+    t.append(time.perf_counter())
     L.ptm_lrgb_finish(C.byref(info), blocks[1].ctypes.data, coeffs.ctypes.data)
+    t.append(time.perf_counter())
     L.ptm_scale_coefficients(C.byref(header), coeffs.ctypes.data, _block_ptrs(blocks))
+    t.append(time.perf_counter())
+    names = ("ptm_fit_poly_jsample", "ptm_cbcr_avg", "ptm_lrgb_finish", "ptm_scale_coefficients")
     return dict(coef=blocks[0].reshape(H, W, PTM_COEFFICIENTS), rgb=blocks[1].reshape(H, W, RGB_COEFFICIENTS),
-                scale=np.array(header.scale, np.float32), bias=np.array(header.bias, np.int32), coeffs=coeffs)
+                scale=np.array(header.scale, np.float32), bias=np.array(header.bias, np.int32), coeffs=coeffs,
+                ms={n: 1e3 * (b - a) for n, a, b in zip(names, t, t[1:])})
