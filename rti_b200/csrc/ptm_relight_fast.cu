@@ -101,54 +101,63 @@ __device__ __forceinline__ f32x2 poly2(const f32x2 *c, const LightPairs &l) {
 }
 
 // bytes p0r p0g p0b p1r | p1g p1b p2r p2g | p2b p3r p3g p3b from z[pair][channel][pixel of the pair]
-__device__ __forceinline__ void words12(const int (&z)[2][3][2], unsigned (&w)[3]) {
+__device__ __forceinline__ void words12(const int (*z)[3][2], unsigned *w) {
     w[0] = bytes4(z[0][0][0], z[0][1][0], z[0][2][0], z[0][0][1]);
     w[1] = bytes4(z[0][1][1], z[0][2][1], z[1][0][0], z[1][1][0]);
     w[2] = bytes4(z[1][2][0], z[1][0][1], z[1][1][1], z[1][2][1]);
 }
 
-// A lane's 12 output bytes of one direction leave the SM in one of two ways:
-//   narrow  three 4-byte stores per lane.  A warp instruction then touches twelve 32-byte sectors with 8-12 bytes
-//           each: every sector of the raster is written by three separate partial stores that L2 has to merge.
-//   wide    the warp's 384 contiguous bytes are transposed through 384 bytes of shared memory (three conflict-free
-//           4-byte stores per lane, one 16-byte load by lanes 0..23) and leave as ONE 16-byte store per lane:
-//           whole sectors, a third of the L2 write transactions.  Double buffered by direction parity, so one
-//           __syncwarp per direction orders the shared-memory accesses.
-template <bool kWide>
-__device__ __forceinline__ void store_dir(const unsigned (&w)[3], uint32_t *dst_lane, uint4 *dst_warp, uint32_t *stage,
+// A lane's output bytes of one direction (kWords 4-byte words: 3 for 4 pixels, 6 for 8) leave the SM in one of two ways:
+//   narrow  4-byte stores.  A warp instruction then touches many 32-byte sectors with 8-12 bytes each: every sector
+//           of the raster is written by three separate partial stores that L2 has to merge.
+//   wide    the warp's contiguous bytes are transposed through shared memory (conflict-free 4-byte stores, lane stride
+//           kWords words; 16-byte loads) and leave as 16-byte stores: whole sectors, a third of the L2 write
+//           transactions.  Double buffered by direction parity, so one __syncwarp per direction orders the accesses.
+template <bool kWide, int kWords>
+__device__ __forceinline__ void store_dir(const unsigned (&w)[kWords], uint32_t *dst_lane, uint4 *dst_warp, uint32_t *stage,
                                           unsigned lane, unsigned d) {
     if (!kWide) {
-        __stcs(dst_lane + 0, w[0]);
-        __stcs(dst_lane + 1, w[1]);
-        __stcs(dst_lane + 2, w[2]);
+#pragma unroll
+        for (int j = 0; j < kWords; ++j)
+            __stcs(dst_lane + j, w[j]);
         return;
     }
-    uint32_t *buf = stage + (d & 1u) * 96u;
-    buf[3 * lane + 0] = w[0];
-    buf[3 * lane + 1] = w[1];
-    buf[3 * lane + 2] = w[2];
+    uint32_t *buf = stage + (d & 1u) * (32u * kWords);
+    if (kWords == 6) {   // 24-byte records: 8-byte shared stores are conflict free, 4-byte ones at stride 6 are not
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            reinterpret_cast<uint2 *>(buf)[3 * lane + j] = make_uint2(w[2 * j], w[2 * j + 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kWords; ++j)
+            buf[kWords * lane + j] = w[j];
+    }
     __syncwarp();
-    if (lane < 24)
-        __stcs(dst_warp + lane, reinterpret_cast<const uint4 *>(buf)[lane]);
+#pragma unroll
+    for (int r = 0; r < (kWords * 8 + 31) / 32; ++r)   // kWords * 32 words = kWords * 8 uint4
+        if (lane + 32 * r < kWords * 8)
+            __stcs(dst_warp + lane + 32 * r, reinterpret_cast<const uint4 *>(buf)[lane + 32 * r]);
 }
 
-constexpr unsigned kWarpsPerBlock = kThreads / 32;
-constexpr size_t kStageBytes = (size_t) kWarpsPerBlock * 2 * 96 * sizeof(uint32_t);   // 6 KB per block
+__host__ __device__ constexpr size_t stage_bytes(int block_threads, int words) { return (size_t) (block_threads / 32) * 2 * 32 * words * 4; }
 
-// LRGB, 4 consecutive pixels of an output row per thread (width % 4 == 0); a warp owns 128 consecutive pixels.
+// LRGB: kQ groups of 4 consecutive pixels of an output row per thread (kQ = 1: 4 pixels, a warp owns 128 consecutive
+// pixels = 384 output bytes per direction; kQ = 2: 8 pixels, 768 bytes per warp and direction -- half as many jumps
+// between the rasters of different directions, which lie 72 MB apart).
 // kDebug (only instantiated in -DPTM_TUNING builds, results are NOT produced): 1 = arithmetic without the stores,
-// 2 = the stores without the arithmetic, 3 = as 2 with default-policy stores instead of streaming ones.
-template <bool kWide, bool kPrefetch, int kDebug = 0>
-__global__ void __launch_bounds__(kThreads, 3)
+// 2 = the stores without the arithmetic, 3 = as 2 with default-policy stores, 5 = as 2 with the rasters 3 KB apart.
+template <int kQ, bool kWide, bool kPrefetch, int kDebug = 0>
+__global__ void __launch_bounds__(256 / kQ, kQ == 1 ? 3 : 4)
 relight_lrgb_fast_kernel(RelightArgs a) {
+    constexpr int kPx = 4 * kQ, kWords = 3 * kQ, kPairs = 2 * kQ;
     extern __shared__ __align__(16) float smem_f[];
-    uint32_t *stage = reinterpret_cast<uint32_t *>(smem_f) + (threadIdx.x >> 5) * 192;
-    float *light_s = smem_f + kStageBytes / sizeof(float);
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smem_f) + (threadIdx.x >> 5) * (2 * 32 * kWords);
+    float *light_s = smem_f + stage_bytes(256 / kQ, kWords) / sizeof(float);
     load_lights(light_s, a);
 
     const size_t pixels = a.width * a.height;
-    const size_t groups = pixels / 4;
-    const size_t gw = a.width / 4;
+    const size_t groups = pixels / kPx;
+    const size_t gw = a.width / kPx;
     const unsigned lane = threadIdx.x & 31;
     unsigned dbg = 0;
     (void) dbg;
@@ -167,72 +176,79 @@ relight_lrgb_fast_kernel(RelightArgs a) {
         const bool whole_warp = gb + 32 <= groups;
         const size_t gs = live ? g : groups - 1;
         const size_t y = gs / gw, xg = gs - y * gw;
-        const size_t p = (a.height - 1 - y) * a.width + xg * 4;   // stored row height-1-y (:587-589)
+        const size_t p = (a.height - 1 - y) * a.width + xg * kPx;   // stored row height-1-y (:587-589)
         const uint2 *c2 = reinterpret_cast<const uint2 *>(a.plane[0] + p * PTM_NCOEF);
         const uint32_t *r32 = reinterpret_cast<const uint32_t *>(a.plane[1] + p * 3);
-        const uint2 cw[3] = {__ldg(c2), __ldg(c2 + 1), __ldg(c2 + 2)};
-        const uint32_t rw[3] = {__ldg(r32), __ldg(r32 + 1), __ldg(r32 + 2)};
-        const uint32_t cb[6] = {cw[0].x, cw[0].y, cw[1].x, cw[1].y, cw[2].x, cw[2].y};
-        float u[4][PTM_NCOEF], col[4][3];
+        f32x2 A[kPairs][PTM_NCOEF], C[kPairs][3];
 #pragma unroll
-        for (int j = 0; j < 24; ++j) {
-            const float m = __uint_as_float(__byte_perm(cb[j >> 2], 0x4B000000u, 0x7650u + (j & 3)));
-            u[j / 6][j % 6] = sc[j % 6] * (m - kb[j % 6]);
+        for (int q = 0; q < kQ; ++q) {
+            const uint2 cw[3] = {__ldg(c2 + 3 * q), __ldg(c2 + 3 * q + 1), __ldg(c2 + 3 * q + 2)};
+            const uint32_t rw[3] = {__ldg(r32 + 3 * q), __ldg(r32 + 3 * q + 1), __ldg(r32 + 3 * q + 2)};
+            const uint32_t cb[6] = {cw[0].x, cw[0].y, cw[1].x, cw[1].y, cw[2].x, cw[2].y};
+            float u[4][PTM_NCOEF], col[4][3];
+#pragma unroll
+            for (int j = 0; j < 24; ++j) {
+                const float m = __uint_as_float(__byte_perm(cb[j >> 2], 0x4B000000u, 0x7650u + (j & 3)));
+                u[j / 6][j % 6] = sc[j % 6] * (m - kb[j % 6]);
+            }
+#pragma unroll
+            for (int j = 0; j < 12; ++j)
+                col[j / 3][j % 3] = byte_to_float(rw[j >> 2], 0x7650u + (j & 3)) * kTwoM75;   // exact
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int k = 0; k < PTM_NCOEF; ++k)
+                    A[2 * q + h][k] = pk(u[2 * h][k], u[2 * h + 1][k]);
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+                    C[2 * q + h][ch] = pk(col[2 * h][ch], col[2 * h + 1][ch]);
+            }
         }
-#pragma unroll
-        for (int j = 0; j < 12; ++j)
-            col[j / 3][j % 3] = byte_to_float(rw[j >> 2], 0x7650u + (j & 3)) * kTwoM75;   // exact
-        f32x2 A[2][PTM_NCOEF], C[2][3];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-#pragma unroll
-            for (int k = 0; k < PTM_NCOEF; ++k)
-                A[h][k] = pk(u[2 * h][k], u[2 * h + 1][k]);
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch)
-                C[h][ch] = pk(col[2 * h][ch], col[2 * h + 1][ch]);
-        }
-        uint32_t *dst = reinterpret_cast<uint32_t *>(a.out + gs * 12);
-        uint4 *dst_warp = reinterpret_cast<uint4 *>(a.out + gb * 12);
-        const size_t dir_words = pixels * 3 / 4;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(a.out + gs * (kPx * 3));
+        uint4 *dst_warp = reinterpret_cast<uint4 *>(a.out + gb * (kPx * 3));
+        const size_t dir_words = kDebug == 5 ? (size_t) (blockDim.x / 32) * 32 * kWords : pixels * 3 / 4;
         // kPrefetch: the light pairs of direction d + 1 are requested from shared memory before direction d is
         // evaluated (the table has a spare entry, so no bounds test)
         LightPairs l = light_pairs(light_s, 0);
-#pragma unroll 2
+#pragma unroll(kQ == 1 ? 2 : 1)
         for (unsigned d = 0; d < a.n_dirs; ++d) {
             LightPairs nxt;
             if (kPrefetch)
                 nxt = light_pairs(light_s, d + 1);
             else
                 l = light_pairs(light_s, d);
-            unsigned w[3];
+            unsigned w[kWords];
             if (kDebug >= 2) {
-                w[0] = d + lane;
-                w[1] = d * 3 + lane;
-                w[2] = d ^ lane;
-            } else {
-                int z[2][3][2];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int j = 0; j < kWords; ++j)
+                    w[j] = d * (j + 1) + lane;
+            } else {
+                int z[kPairs][3][2];
+#pragma unroll
+                for (int h = 0; h < kPairs; ++h) {
                     const f32x2 L = poly2(A[h], l);
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch)
                         unpk_bits(mul2_rz(L, C[h][ch]), z[h][ch][0], z[h][ch][1]);   // (L 2^-74)(c 2^-75): bits = floor(L c)
                 }
-                words12(z, w);
+#pragma unroll
+                for (int q = 0; q < kQ; ++q)
+                    words12(z + 2 * q, w + 3 * q);
             }
             if (kDebug == 1) {
-                dbg ^= w[0] + w[1] + w[2];
+#pragma unroll
+                for (int j = 0; j < kWords; ++j)
+                    dbg ^= w[j];
             } else if (kDebug == 3) {
                 if (live) {
-                    dst[0] = w[0];
-                    dst[1] = w[1];
-                    dst[2] = w[2];
+#pragma unroll
+                    for (int j = 0; j < kWords; ++j)
+                        dst[j] = w[j];
                 }
             } else if (kWide && whole_warp) {
-                store_dir<true>(w, dst, dst_warp, stage, lane, d);
+                store_dir<true, kWords>(w, dst, dst_warp, stage, lane, d);
             } else if (live) {
-                store_dir<false>(w, dst, dst_warp, stage, lane, d);
+                store_dir<false, kWords>(w, dst, dst_warp, stage, lane, d);
             }
             dst += dir_words;
             dst_warp += dir_words / 4;
@@ -252,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 relight_rgb_fast_kernel(RelightArgs a) {
     extern __shared__ __align__(16) float smem_f[];
     uint32_t *stage = reinterpret_cast<uint32_t *>(smem_f) + (threadIdx.x >> 5) * 192;
-    float *light_s = smem_f + kStageBytes / sizeof(float);
+    float *light_s = smem_f + stage_bytes(kThreads, 3) / sizeof(float);
     load_lights(light_s, a);
 
     const size_t pixels = a.width * a.height;
@@ -309,9 +325,9 @@ relight_rgb_fast_kernel(RelightArgs a) {
             unsigned w[3];
             words12(z, w);
             if (kWide && whole_warp)
-                store_dir<true>(w, dst, dst_warp, stage, lane, d);
+                store_dir<true, 3>(w, dst, dst_warp, stage, lane, d);
             else if (live)
-                store_dir<false>(w, dst, dst_warp, stage, lane, d);
+                store_dir<false, 3>(w, dst, dst_warp, stage, lane, d);
             dst += dir_words;
             dst_warp += dir_words / 4;
             if (kPrefetch)
@@ -339,19 +355,21 @@ cudaError_t launch_relight_fast(const RelightArgs &a, bool lrgb, int sm_count, c
         ok = ok && ((uintptr_t) a.plane[1] % 8 == 0) && ((uintptr_t) a.plane[2] % 8 == 0);
     if (!ok)
         return cudaErrorNotSupported;
-    const size_t want = (pixels / 4 + kThreads - 1) / kThreads;
-    const size_t smem = kStageBytes + ((size_t) a.n_dirs + 1) * 12 * sizeof(float);
     // tuning aid (result-equivalent kernel shapes): bit 0 = 16-byte stores through a shared-memory transpose,
-    // bit 1 = light table look-ahead.  The default is what measured fastest.
+    // bit 1 = light table look-ahead, bit 2 (LRGB) = 8 pixels per thread.  The default is what measured fastest.
     static int variant = -1;
     if (variant < 0) {
         const char *v = getenv("PTM_RELIGHT_VARIANT");
-        variant = v ? atoi(v) & 3 : kDefaultVariant;
+        variant = v ? atoi(v) & 7 : kDefaultVariant;
     }
     const bool wide = (variant & 1) && ((uintptr_t) a.out % 16 == 0) && (pixels * 3) % 16 == 0;
     const int vsel = (wide ? 1 : 0) | (variant & 2);
     if (lrgb) {
-        const size_t cap = (size_t) sm_count * 8;
+        const bool q2 = (variant & 4) && a.width % 8 == 0 && ((uintptr_t) a.plane[1] % 8 == 0);
+        const int threads = q2 ? 128 : 256, px = q2 ? 8 : 4;
+        const size_t want = (pixels / px + threads - 1) / threads;
+        const size_t smem = stage_bytes(threads, q2 ? 6 : 3) + ((size_t) a.n_dirs + 1) * 12 * sizeof(float);
+        const size_t cap = (size_t) sm_count * (q2 ? 4 : 3);   // one resident wave; the grid-stride loop does the rest
         const unsigned grid = (unsigned) (want < cap ? want : cap);
 #ifdef PTM_TUNING
         static int debug = -1;
@@ -359,18 +377,43 @@ cudaError_t launch_relight_fast(const RelightArgs &a, bool lrgb, int sm_count, c
             const char *v = getenv("PTM_RELIGHT_DEBUG");
             debug = v ? atoi(v) : 0;
         }
-        if (debug == 1) { relight_lrgb_fast_kernel<false, false, 1><<<grid, kThreads, smem, st>>>(a); return cudaGetLastError(); }
-        if (debug == 2) { relight_lrgb_fast_kernel<false, false, 2><<<grid, kThreads, smem, st>>>(a); return cudaGetLastError(); }
-        if (debug == 3) { relight_lrgb_fast_kernel<false, false, 3><<<grid, kThreads, smem, st>>>(a); return cudaGetLastError(); }
-        if (debug == 4) { relight_lrgb_fast_kernel<true, false, 2><<<grid, kThreads, smem, st>>>(a); return cudaGetLastError(); }
+#define PTM_DBG(Q, W, D)                                                                              \
+    {                                                                                                 \
+        relight_lrgb_fast_kernel<Q, W, false, D><<<grid, threads, smem, st>>>(a);                     \
+        return cudaGetLastError();                                                                    \
+    }
+        if (debug && !q2) {
+            if (debug == 1) PTM_DBG(1, false, 1)
+            if (debug == 2) PTM_DBG(1, false, 2)
+            if (debug == 3) PTM_DBG(1, false, 3)
+            if (debug == 4) PTM_DBG(1, true, 2)
+            if (debug == 5) PTM_DBG(1, true, 5)
+        } else if (debug) {
+            if (debug == 1) PTM_DBG(2, false, 1)
+            if (debug == 2) PTM_DBG(2, false, 2)
+            if (debug == 4) PTM_DBG(2, true, 2)
+            if (debug == 5) PTM_DBG(2, true, 5)
+        }
+#undef PTM_DBG
 #endif
-        switch (vsel) {
-        case 0: relight_lrgb_fast_kernel<false, false><<<grid, kThreads, smem, st>>>(a); break;
-        case 1: relight_lrgb_fast_kernel<true, false><<<grid, kThreads, smem, st>>>(a); break;
-        case 2: relight_lrgb_fast_kernel<false, true><<<grid, kThreads, smem, st>>>(a); break;
-        default: relight_lrgb_fast_kernel<true, true><<<grid, kThreads, smem, st>>>(a); break;
+        if (q2) {
+            switch (vsel) {
+            case 0: relight_lrgb_fast_kernel<2, false, false><<<grid, threads, smem, st>>>(a); break;
+            case 1: relight_lrgb_fast_kernel<2, true, false><<<grid, threads, smem, st>>>(a); break;
+            case 2: relight_lrgb_fast_kernel<2, false, true><<<grid, threads, smem, st>>>(a); break;
+            default: relight_lrgb_fast_kernel<2, true, true><<<grid, threads, smem, st>>>(a); break;
+            }
+        } else {
+            switch (vsel) {
+            case 0: relight_lrgb_fast_kernel<1, false, false><<<grid, threads, smem, st>>>(a); break;
+            case 1: relight_lrgb_fast_kernel<1, true, false><<<grid, threads, smem, st>>>(a); break;
+            case 2: relight_lrgb_fast_kernel<1, false, true><<<grid, threads, smem, st>>>(a); break;
+            default: relight_lrgb_fast_kernel<1, true, true><<<grid, threads, smem, st>>>(a); break;
+            }
         }
     } else {
+        const size_t want = (pixels / 4 + kThreads - 1) / kThreads;
+        const size_t smem = stage_bytes(kThreads, 3) + ((size_t) a.n_dirs + 1) * 12 * sizeof(float);
         const size_t cap = (size_t) sm_count * 2;
         const unsigned grid = (unsigned) (want < cap ? want : cap);
         switch (vsel) {
