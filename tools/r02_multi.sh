@@ -1,0 +1,17 @@
+#!/bin/bash
+# round 2, multi-GPU call: N = $1 GPUs.  2-GPU pytest (in-process multi + torchrun-style), bench both drivers, reference arm.
+N=${1:-2}
+O=gpurun_out
+mkdir -p $O
+nvidia-smi topo -m > $O/r02m_topo_n$N.txt 2>&1
+timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -s > $O/r02m_pytest_multi_n$N.log 2>&1
+echo "pytest rc=$?" >> $O/r02m_pytest_multi_n$N.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+    bench.py --gpus $N --steps 20 --warmup 3 > $O/r02m_bench_torchrun_n$N.json 2> $O/r02m_bench_torchrun_n$N.err
+echo "torchrun rc=$?" >> $O/r02m_bench_torchrun_n$N.err
+timeout 900 python bench.py --gpus $N --driver c --steps 20 --warmup 3 > $O/r02m_bench_c_n$N.json 2> $O/r02m_bench_c_n$N.err
+echo "driver c rc=$?" >> $O/r02m_bench_c_n$N.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
+    bench.py --impl reference --gpus $N --steps 3 --warmup 1 > $O/r02m_bench_ref_n$N.json 2> $O/r02m_bench_ref_n$N.err
+tail -8 $O/r02m_pytest_multi_n$N.log
+for f in torchrun c ref; do echo "== $f"; cut -c1-1500 $O/r02m_bench_${f}_n$N.json; tail -3 $O/r02m_bench_${f}_n$N.err; done
