@@ -75,6 +75,10 @@ int ptmb_upload (ptmb_ctx_t *ctx, void *dev, const void *host, size_t bytes);
 int ptmb_download (ptmb_ctx_t *ctx, void *host, const void *dev, size_t bytes);
 int ptmb_host_register (const void *host, size_t bytes);
 int ptmb_host_unregister (const void *host);
+/* Pinned host memory usable from every GPU of the process (cudaHostAllocPortable).  write_combined: faster for the
+ * GPU to read over PCIe on some hosts, but very slow for the CPU to READ -- only for buffers the CPU just fills. */
+int ptmb_host_alloc (size_t bytes, int write_combined, void **host);
+int ptmb_host_free (void *host);
 
 /* The 6 x n_lights pseudo-inverse from ptm_svd (rti-builder/ptmlib.c:630-689), row
  * major, HOST pointer.  Copied to the device; valid for all later fits. */

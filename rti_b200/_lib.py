@@ -43,6 +43,8 @@ _SIGNATURES = {
     "ptmb_download": ([_vp, _vp, _vp, _sz], _int),
     "ptmb_host_register": ([_vp, _sz], _int),
     "ptmb_host_unregister": ([_vp], _int),
+    "ptmb_host_alloc": ([_sz, _int, C.POINTER(_vp)], _int),
+    "ptmb_host_free": ([_vp], _int),
     "ptmb_set_matrix": ([_vp, _vp, C.c_uint], _int),
     "ptmb_set_fit_engine": ([_vp, _int], _int),
     "ptmb_mma_launches": ([], C.c_ulonglong),

@@ -176,6 +176,18 @@ int ptmb_host_register(const void *host, size_t bytes) {
     return 0;
 }
 
+int ptmb_host_alloc(size_t bytes, int write_combined, void **host) {
+    REQUIRE(host, "NULL argument");
+    CK(cudaHostAlloc(host, bytes ? bytes : 1,
+                     cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault)));
+    return 0;
+}
+
+int ptmb_host_free(void *host) {
+    CK(cudaFreeHost(host));
+    return 0;
+}
+
 int ptmb_host_unregister(const void *host) {
     CK(cudaHostUnregister(const_cast<void *>(host)));
     return 0;

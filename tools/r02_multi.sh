@@ -11,7 +11,9 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 echo "torchrun rc=$?" >> $O/r02m_bench_torchrun_n$N.err
 timeout 900 python bench.py --gpus $N --driver c --steps 20 --warmup 3 > $O/r02m_bench_c_n$N.json 2> $O/r02m_bench_c_n$N.err
 echo "driver c rc=$?" >> $O/r02m_bench_c_n$N.err
+timeout 600 python tools/ubench_h2d_multi.py $N 1.0 $2 > $O/r02m_ubench_h2d_n$N.txt 2>&1
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
     bench.py --impl reference --gpus $N --steps 3 --warmup 1 > $O/r02m_bench_ref_n$N.json 2> $O/r02m_bench_ref_n$N.err
 tail -8 $O/r02m_pytest_multi_n$N.log
 for f in torchrun c ref; do echo "== $f"; cut -c1-1500 $O/r02m_bench_${f}_n$N.json; tail -3 $O/r02m_bench_${f}_n$N.err; done
+cat $O/r02m_ubench_h2d_n$N.txt | grep aggregate
