@@ -30,7 +30,8 @@ namespace ptm {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kDefaultVariant = 1;
+constexpr int kDefaultVariant = 5;      // LRGB: 8 pixels per thread, 16-byte stores (4.58 ms for 24 MP x 360)
+constexpr int kDefaultRgbVariant = 0;   // RGB formats: 4-byte stores (the transposition costs more than it saves there)
 
 typedef unsigned long long f32x2;
 
@@ -262,128 +263,6 @@ relight_lrgb_fast_kernel(RelightArgs a) {
         a.out[0] = 1;
 }
 
-// LRGB with BLOCK-level output staging.  The rasters of different directions lie width * height * 3 bytes apart
-// (72 MB at 24 MP), so a warp that writes its own 384 / 768 bytes of direction d and then jumps to direction d + 1
-// asks for a new page translation with every store instruction: measured with the stores alone, that pattern moves
-// 5.6-6.1 TB/s, the same instructions on a 3 KB raster pitch 7.7 TB/s (tools/r02_run6.sh).  Here a block
-// computes kBatch directions for its 1024 pixels into shared memory ([direction][3 KB], the output layout), and after
-// one barrier warp w copies direction w's 3 KB to global memory as six consecutive 16-byte-per-lane stores -- one
-// translation per 3 KB instead of one per store.  Double buffered: the next batch is computed while the copies drain.
-template <int kQ, int kDebug = 0>
-__global__ void __launch_bounds__(256 / kQ, kQ == 1 ? 3 : 4)
-relight_lrgb_bflush_kernel(RelightArgs a) {
-    constexpr int kPx = 4 * kQ, kWords = 3 * kQ, kPairs = 2 * kQ, kBlock = 256 / kQ, kBatch = kBlock / 32;
-    constexpr int kDirWords = kBlock * kWords;   // 768 words = 3 KB of one direction
-    extern __shared__ __align__(16) float smem_f[];
-    uint32_t *stage = reinterpret_cast<uint32_t *>(smem_f);                 // [2][kBatch][kDirWords]
-    float *light_s = smem_f + 2 * kBatch * kDirWords;
-    load_lights(light_s, a);
-
-    const size_t pixels = a.width * a.height;
-    const size_t groups = pixels / kPx;
-    const size_t gw = a.width / kPx;
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float sc[PTM_NCOEF], kb[PTM_NCOEF];
-#pragma unroll
-    for (int k = 0; k < PTM_NCOEF; ++k) {
-        sc[k] = (a.scale[k] * 0.003921568627450980392f) * kTwoM74;   // scale_k / 255 * 2^-74, see above
-        kb[k] = 8388608.0f + (float) a.bias[k];
-    }
-    const size_t dir_bytes = kDebug == 5 ? (size_t) kDirWords * 4 : pixels * 3;
-    unsigned batch = 0;
-    for (size_t bb = (size_t) blockIdx.x * kBlock; bb < groups; bb += (size_t) gridDim.x * kBlock) {   // block uniform
-        const size_t g = bb + threadIdx.x;
-        const bool live = g < groups;
-        const bool whole_block = bb + kBlock <= groups;
-        const size_t gs = live ? g : groups - 1;
-        const size_t y = gs / gw, xg = gs - y * gw;
-        const size_t p = (a.height - 1 - y) * a.width + xg * kPx;   // stored row height-1-y (:587-589)
-        const uint2 *c2 = reinterpret_cast<const uint2 *>(a.plane[0] + p * PTM_NCOEF);
-        const uint32_t *r32 = reinterpret_cast<const uint32_t *>(a.plane[1] + p * 3);
-        f32x2 A[kPairs][PTM_NCOEF], C[kPairs][3];
-#pragma unroll
-        for (int q = 0; q < kQ; ++q) {
-            const uint2 cw[3] = {__ldg(c2 + 3 * q), __ldg(c2 + 3 * q + 1), __ldg(c2 + 3 * q + 2)};
-            const uint32_t rw[3] = {__ldg(r32 + 3 * q), __ldg(r32 + 3 * q + 1), __ldg(r32 + 3 * q + 2)};
-            const uint32_t cb[6] = {cw[0].x, cw[0].y, cw[1].x, cw[1].y, cw[2].x, cw[2].y};
-            float u[4][PTM_NCOEF], col[4][3];
-#pragma unroll
-            for (int j = 0; j < 24; ++j) {
-                const float m = __uint_as_float(__byte_perm(cb[j >> 2], 0x4B000000u, 0x7650u + (j & 3)));
-                u[j / 6][j % 6] = sc[j % 6] * (m - kb[j % 6]);
-            }
-#pragma unroll
-            for (int j = 0; j < 12; ++j)
-                col[j / 3][j % 3] = byte_to_float(rw[j >> 2], 0x7650u + (j & 3)) * kTwoM75;   // exact
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                for (int k = 0; k < PTM_NCOEF; ++k)
-                    A[2 * q + h][k] = pk(u[2 * h][k], u[2 * h + 1][k]);
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch)
-                    C[2 * q + h][ch] = pk(col[2 * h][ch], col[2 * h + 1][ch]);
-            }
-        }
-        uint8_t *out_block = a.out + bb * (kPx * 3);
-        uint32_t *dst_lane = reinterpret_cast<uint32_t *>(a.out + gs * (kPx * 3));
-        for (unsigned d0 = 0; d0 < a.n_dirs; d0 += kBatch, ++batch) {
-            const unsigned nb = min((unsigned) kBatch, a.n_dirs - d0);
-            uint32_t *buf = stage + (batch & 1u) * (kBatch * kDirWords);
-#pragma unroll(kQ == 1 ? 2 : 1)
-            for (unsigned j = 0; j < nb; ++j) {
-                const unsigned d = d0 + j;
-                unsigned w[kWords];
-                if (kDebug >= 2) {
-#pragma unroll
-                    for (int i = 0; i < kWords; ++i)
-                        w[i] = d * (i + 1) + lane;
-                } else {
-                    const LightPairs l = light_pairs(light_s, d);
-                    int z[kPairs][3][2];
-#pragma unroll
-                    for (int h = 0; h < kPairs; ++h) {
-                        const f32x2 L = poly2(A[h], l);
-#pragma unroll
-                        for (int ch = 0; ch < 3; ++ch)
-                            unpk_bits(mul2_rz(L, C[h][ch]), z[h][ch][0], z[h][ch][1]);   // bits = floor(L c)
-                    }
-#pragma unroll
-                    for (int q = 0; q < kQ; ++q)
-                        words12(z + 2 * q, w + 3 * q);
-                }
-                if (whole_block) {
-                    uint32_t *row = buf + j * kDirWords + threadIdx.x * kWords;
-                    if (kWords == 6) {   // 8-byte shared stores: conflict free at a lane stride of 24 bytes
-#pragma unroll
-                        for (int i = 0; i < 3; ++i)
-                            reinterpret_cast<uint2 *>(row)[i] = make_uint2(w[2 * i], w[2 * i + 1]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < kWords; ++i)
-                            row[i] = w[i];
-                    }
-                } else if (live) {   // the image's last, partial block: straight from the registers
-                    uint32_t *dl = dst_lane + (size_t) d * (dir_bytes / 4);
-#pragma unroll
-                    for (int i = 0; i < kWords; ++i)
-                        __stcs(dl + i, w[i]);
-                }
-            }
-            if (whole_block) {
-                __syncthreads();   // the batch is complete; also: every warp has finished copying the batch before last
-                if (warp < nb) {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(buf + warp * kDirWords);
-                    uint4 *dst = reinterpret_cast<uint4 *>(out_block + (size_t) (d0 + warp) * dir_bytes);
-#pragma unroll
-                    for (int r = 0; r < kDirWords / 4 / 32; ++r)
-                        __stcs(dst + lane + 32 * r, src[lane + 32 * r]);
-                }
-            }
-        }
-    }
-}
-
 // RGB formats, 4 consecutive pixels per thread: CLIP(POLY) per channel (rti-builder/ptmlib.c:610-619).
 template <bool kWide, bool kPrefetch>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -432,6 +311,7 @@ relight_rgb_fast_kernel(RelightArgs a) {
         uint4 *dst_warp = reinterpret_cast<uint4 *>(a.out + gb * 12);
         const size_t dir_words = pixels * 3 / 4;
         LightPairs l = light_pairs(light_s, 0);
+#pragma unroll(kPrefetch ? 1 : 2)
         for (unsigned d = 0; d < a.n_dirs; ++d) {
             LightPairs nxt;
             if (kPrefetch)
@@ -482,10 +362,16 @@ cudaError_t launch_relight_fast(const RelightArgs &a, bool lrgb, int sm_count, c
     static int variant = -1;
     if (variant < 0) {
         const char *v = getenv("PTM_RELIGHT_VARIANT");
-        variant = v ? atoi(v) & 15 : kDefaultVariant;
+        variant = v ? atoi(v) & 7 : kDefaultVariant;
     }
-    const bool wide = (variant & 1) && ((uintptr_t) a.out % 16 == 0) && (pixels * 3) % 16 == 0;
-    const int vsel = (wide ? 1 : 0) | (variant & 2);
+    static int rgb_variant = -1;
+    if (rgb_variant < 0) {
+        const char *v = getenv("PTM_RELIGHT_RGB_VARIANT");
+        rgb_variant = v ? atoi(v) & 3 : kDefaultRgbVariant;
+    }
+    const int var = lrgb ? variant : rgb_variant;
+    const bool wide = (var & 1) && ((uintptr_t) a.out % 16 == 0) && (pixels * 3) % 16 == 0;
+    const int vsel = (wide ? 1 : 0) | (var & 2);
     if (lrgb) {
         const bool q2 = (variant & 4) && a.width % 8 == 0 && ((uintptr_t) a.plane[1] % 8 == 0);
         const int threads = q2 ? 128 : 256, px = q2 ? 8 : 4;
@@ -500,48 +386,6 @@ cudaError_t launch_relight_fast(const RelightArgs &a, bool lrgb, int sm_count, c
             debug = v ? atoi(v) : 0;
         }
 #endif
-        if (variant & 8) {   // block-level output staging
-            const bool okb = wide;   // same alignment conditions
-            if (okb) {
-                const size_t bsmem = 2 * (size_t) (threads / 32) * (threads * (q2 ? 6 : 3)) * 4 +
-                                     ((size_t) a.n_dirs + 1) * 12 * sizeof(float);
-                static bool allowed[64] = {};
-                int dev = 0;
-                cudaError_t e = cudaGetDevice(&dev);
-                if (e != cudaSuccess)
-                    return e;
-                if (dev >= 0 && dev < 64 && !allowed[dev]) {
-                    const int mx = 2 * 8 * 3072 + 1024 * 48;
-                    if ((e = cudaFuncSetAttribute(relight_lrgb_bflush_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess ||
-                        (e = cudaFuncSetAttribute(relight_lrgb_bflush_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess)
-                        return e;
-#ifdef PTM_TUNING
-                    cudaFuncSetAttribute(relight_lrgb_bflush_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-                    cudaFuncSetAttribute(relight_lrgb_bflush_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-                    cudaFuncSetAttribute(relight_lrgb_bflush_kernel<1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-                    cudaFuncSetAttribute(relight_lrgb_bflush_kernel<2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-#endif
-                    allowed[dev] = true;
-                }
-#ifdef PTM_TUNING
-                if (debug == 2 || debug == 4) {
-                    if (q2) relight_lrgb_bflush_kernel<2, 2><<<grid, threads, bsmem, st>>>(a);
-                    else relight_lrgb_bflush_kernel<1, 2><<<grid, threads, bsmem, st>>>(a);
-                    return cudaGetLastError();
-                }
-                if (debug == 5) {
-                    if (q2) relight_lrgb_bflush_kernel<2, 5><<<grid, threads, bsmem, st>>>(a);
-                    else relight_lrgb_bflush_kernel<1, 5><<<grid, threads, bsmem, st>>>(a);
-                    return cudaGetLastError();
-                }
-#endif
-                if (q2)
-                    relight_lrgb_bflush_kernel<2><<<grid, threads, bsmem, st>>>(a);
-                else
-                    relight_lrgb_bflush_kernel<1><<<grid, threads, bsmem, st>>>(a);
-                return cudaGetLastError();
-            }
-        }
 #ifdef PTM_TUNING
 #define PTM_DBG(Q, W, D)                                                                              \
     {                                                                                                 \

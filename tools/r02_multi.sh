@@ -17,3 +17,8 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 tail -8 $O/r02m_pytest_multi_n$N.log
 for f in torchrun c ref; do echo "== $f"; cut -c1-1500 $O/r02m_bench_${f}_n$N.json; tail -3 $O/r02m_bench_${f}_n$N.err; done
 cat $O/r02m_ubench_h2d_n$N.txt | grep aggregate
+if [ "$N" = "2" ]; then
+  for v in 0 1 2 3; do PTM_RELIGHT_RGB_VARIANT=$v python tools/relight_once.py 360 rgb fast | sed "s/^/rgb variant $v: /"; done > $O/r02m_relight_rgb.txt 2>&1
+  python tools/relight_once.py 360 lrgb fast >> $O/r02m_relight_rgb.txt 2>&1
+  cat $O/r02m_relight_rgb.txt
+fi
