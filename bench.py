@@ -303,9 +303,58 @@ def sharded_identity(enc, M, L, W, H, r0, r1, world):
     flag = torch.tensor([1 if same else 0], dtype=torch.int32, device="cuda")
     if world > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    blocks = (single.coef_bytes[0].clone(), single.rgb.clone())
     del full, single
     torch.cuda.empty_cache()
-    return bool(flag.item()), digest
+    return bool(flag.item()), digest, blocks
+
+
+def h2d_shares(world, seconds=0.012, chunk=8 << 20):
+    """GB/s every rank gets when ALL ranks copy pinned host memory to their GPU for the same span of time (the GPUs
+    of one box do not share the host's PCIe bandwidth equally: on this pool's 8-GPU boxes four get 23 GB/s and four
+    35 GB/s).  The e2e leg splits the image's rows in these proportions."""
+    import torch
+    import torch.distributed as dist
+    host = torch.empty(2 * chunk, dtype=torch.uint8).pin_memory()
+    dev = torch.empty(2 * chunk, dtype=torch.uint8, device="cuda")
+    dev.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(), torch.cuda.Event()]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    moved, k = 0, 0
+    dev[:chunk].copy_(host[:chunk], non_blocking=True)
+    ev[0].record()
+    while True:
+        k ^= 1
+        dev[k * chunk:(k + 1) * chunk].copy_(host[k * chunk:(k + 1) * chunk], non_blocking=True)
+        ev[k].record()
+        ev[k ^ 1].synchronize()
+        moved += chunk
+        dt = time.perf_counter() - t0
+        if dt >= seconds:
+            break
+    torch.cuda.synchronize()
+    rate = torch.tensor([moved / dt / 1e9], dtype=torch.float64, device="cuda")
+    rates = [torch.zeros_like(rate) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(rates, rate)
+    else:
+        rates = [rate]
+    return [float(r.item()) for r in rates]
+
+
+def weighted_cuts(height, weights):
+    """Row boundaries [c_0 = 0, ..., c_n = height] with slab i ~ weights[i] (formula of ptm_multi.cu: cut)."""
+    total = float(sum(weights))
+    cuts, upto = [0], 0.0
+    for w in weights[:-1]:
+        upto += w
+        cuts.append(min(height, int(height * (upto / total) + 0.5)))
+    cuts.append(height)
+    return cuts
 
 
 # ------------------------------------------------------------------- extras (configs[3], configs[4])
@@ -503,20 +552,37 @@ def run_b200(args):
         step()
     barrier()
 
-    # ---- device-resident timing; the library brackets its fit stage (K1) with CUDA events on the
-    # same stream inside the timed region (ptmb_probe_*), which is what the roofline object uses
+    # ---- device-resident timing.  Nothing but the encodes is enqueued between the two events: an event record
+    # between K1 and K2 would break their programmatic (PDL) chaining, so K1 is timed in a SECOND pass of the same
+    # loop, where the library brackets its fit stage with CUDA events on the launching stream (ptmb_probe_*).
+    # N > 1: one untimed encode right after the barrier lines the ranks up on the device (every K2 waits for all
+    # peers' keys), so the max over ranks does not include the host barrier's release jitter.
     fused = enc.launches_per_encode == 2
-    if fused:
-        enc.ctx.probe_arm(args.steps)
-    else:
-        k1_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                     for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
     if sampler:
         sampler.start()
     barrier()
+    if world > 1:
+        step()
     t_start.record()
+    for i in range(args.steps):
+        step()
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_total = t_start.elapsed_time(t_end)
+
+    p_start, p_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if world > 1:
+        step()
+    if fused:
+        enc.ctx.probe_arm(args.steps)
+    else:
+        k1_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                     for _ in range(args.steps)]
+    p_start.record()
     for i in range(args.steps):
         if fused:
             step()
@@ -526,31 +592,51 @@ def run_b200(args):
             k1_events[i][1].record()
             enc.exchange()
             enc.quantise()
-    t_end.record()
+    p_end.record()
     barrier()
-    clocks = sampler.stop() if sampler else None
-    ms_total = t_start.elapsed_time(t_end)
+    probed_ms = p_start.elapsed_time(p_end) / args.steps
     if fused:
         k1_ms = float(np.mean(enc.ctx.probe_read(args.steps)))
     else:
         k1_ms = float(np.mean([a.elapsed_time(b) for a, b in k1_events]))
+    (probed_ms,) = allmax([probed_ms])
     ms_total, k1_ms = allmax([ms_total, k1_ms])
     ms_step = ms_total / args.steps
     value = W * H / (ms_step * 1e-3) / 1e6
 
-    # ---- end to end through the host-buffer C-ABI call
+    # ---- N > 1: the sharded blocks must equal a single-GPU encode of the whole image
+    sharded, single_blocks = None, None
+    if world > 1:
+        same, digest, single_blocks = sharded_identity(enc, M, L, W, H, r0, r1, world)
+        sharded = {"sharded_identical": same, "single_gpu_blocks_sha256": digest,
+                   "how": "every rank encodes the whole image on its own GPU (no exchange) and compares its slab"}
+
+    # ---- end to end through the host-buffer C-ABI call.  The rows are split over the ranks in proportion to the
+    # host bandwidth each GPU gets when all of them copy at once (measured here, PTM_E2E_BALANCE=0: equal slabs):
+    # this leg is bound by PCIe, not by the kernels, so its slabs follow the links.
     e2e = None
     host_stack = None
     if not args.no_e2e:
         ctx = Context(local, stream=torch.cuda.current_stream().cuda_stream)
-        host_stack = torch.empty((N_LIGHTS, rows, W, 3), dtype=torch.uint8).pin_memory()
-        host_stack.copy_(stack)                               # same synthetic bytes, now in pinned host memory
-        out_coef = torch.empty((rows, W, 6), dtype=torch.uint8).pin_memory()
-        out_rgb = torch.empty((rows, W, 3), dtype=torch.uint8).pin_memory()
+        shares = h2d_shares(world) if world > 1 else [1.0]
+        balanced = world > 1 and os.environ.get("PTM_E2E_BALANCE", "1") == "1"
+        cuts = weighted_cuts(H, shares) if balanced else [slab_rows(H, world, i)[0] for i in range(world)] + [H]
+        e0, e1 = cuts[rank], cuts[rank + 1]
+        erows = e1 - e0
+        if (e0, e1) == (r0, r1):
+            dev_slab = stack
+        else:
+            dev_slab = torch.empty((N_LIGHTS, erows, W, 3), dtype=torch.uint8, device="cuda")
+            enc.ctx.synth(SEED, 0, U8, e0 * W, erows * W, light_q14(L), dev_slab, erows * W * 3)
+            torch.cuda.synchronize()
+        host_stack = torch.empty((N_LIGHTS, erows, W, 3), dtype=torch.uint8).pin_memory()
+        host_stack.copy_(dev_slab)                            # same synthetic bytes, now in pinned host memory
+        out_coef = torch.empty((erows, W, 6), dtype=torch.uint8).pin_memory()
+        out_rgb = torch.empty((erows, W, 3), dtype=torch.uint8).pin_memory()
         keys = torch.empty(12, dtype=torch.int32, device="cuda")
 
-        # the ceiling: the same pinned buffer copied to the device with nothing else going on, all ranks at once
-        scratch = torch.empty_like(stack)
+        # the ceiling: the same pinned buffers copied to the device with nothing else going on, all ranks at once
+        scratch = dev_slab if dev_slab is not stack else torch.empty_like(stack)
         scratch.copy_(host_stack, non_blocking=True)
         barrier()
         ca, cb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -560,11 +646,11 @@ def run_b200(args):
         cb_.record()
         barrier()
         (h2d_ms,) = allmax([ca.elapsed_time(cb_) / 2])
-        del scratch
+        del scratch, dev_slab
         h2d_peak_gbs = N_LIGHTS * W * H * 3 / (h2d_ms * 1e-3) / 1e9     # aggregate over all ranks
 
         def e2e_step():
-            ctx.encode_host_fit(host_stack.data_ptr(), (N_LIGHTS, rows, W), U8, M, planes=1, keys_out=keys,
+            ctx.encode_host_fit(host_stack.data_ptr(), (N_LIGHTS, erows, W), U8, M, planes=1, keys_out=keys,
                                 early_rgb=out_rgb)
             allreduce_keys(keys)
             return ctx.encode_host_finish(keys, [out_coef, out_rgb])
@@ -577,26 +663,28 @@ def run_b200(args):
         barrier()
         (e2e_s,) = allmax([time.perf_counter() - t0])
         e2e_s /= args.e2e_steps
-        # the host path must give the same bytes as the device-resident one
-        assert torch.equal(out_coef.reshape(-1, 6), enc.coef_bytes[0].cpu()), "e2e bytes differ from device path"
-        assert torch.equal(out_rgb.reshape(-1, 3), enc.rgb.cpu()), "e2e colour block differs from device path"
+        # the host path must give the same bytes as the device-resident one (N > 1: as a single-GPU encode of the
+        # whole image, whatever the split)
+        if single_blocks is not None:
+            want_coef, want_rgb = single_blocks[0][e0 * W:e1 * W].cpu(), single_blocks[1][e0 * W:e1 * W].cpu()
+        else:
+            want_coef, want_rgb = enc.coef_bytes[0].cpu(), enc.rgb.cpu()
+        assert torch.equal(out_coef.reshape(-1, 6), want_coef), "e2e bytes differ from device path"
+        assert torch.equal(out_rgb.reshape(-1, 3), want_rgb), "e2e colour block differs from device path"
         h2d_gbs = N_LIGHTS * W * H * 3 / e2e_s / 1e9
         e2e = {"value": W * H / e2e_s / 1e6, "unit": "Mpixel/s",
-               "h2d_bytes_per_step": int(host_stack.numel()), "d2h_bytes_per_step": int(out_coef.numel() + out_rgb.numel()),
+               "h2d_bytes_per_step": int(N_LIGHTS * W * H * 3), "d2h_bytes_per_step": int(W * H * 9),
                "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
                "h2d_gbs": h2d_gbs, "h2d_peak_gbs": h2d_peak_gbs, "frac_of_h2d_peak": h2d_gbs / h2d_peak_gbs,
                "h2d_peak_note": "aggregate rate of plain pinned cudaMemcpyAsync of the same buffers, all ranks at once",
+               "h2d_share_gbs_per_rank": shares if world > 1 else None,
+               "rows_per_rank": [cuts[i + 1] - cuts[i] for i in range(world)],
                "numa_bound_cpus": numa_cpus,
                "identical_to_device_path": True,
-               "note": "per-rank bytes; pinned host stack -> ptmb_encode_host_fit/finish -> pinned host blocks"}
+               "note": "whole-job bytes; every rank: pinned host slab -> ptmb_encode_host_fit/finish -> pinned host "
+                       "blocks; slabs proportional to each GPU's measured share of the host's PCIe bandwidth"}
         ctx.close()
-
-    # ---- N > 1: the sharded blocks must equal a single-GPU encode of the whole image
-    sharded = None
-    if world > 1:
-        same, digest = sharded_identity(enc, M, L, W, H, r0, r1, world)
-        sharded = {"sharded_identical": same, "single_gpu_blocks_sha256": digest,
-                   "how": "every rank encodes the whole image on its own GPU (no exchange) and compares its slab"}
+    del single_blocks
 
     if rank != 0:
         if world > 1:
@@ -627,7 +715,9 @@ def run_b200(args):
                      "algorithmic_bytes_per_px": ALG_BYTES_PATH, "peak_source": peak_src,
                      "traffic": traffic, "traffic_ratio": None if traffic is None else traffic / (ALG_BYTES_PATH * W * H),
                      "traffic_source": traffic_src,
-                     "k1_ms": k1_ms, "k1_achieved": k1_gbs, "k1_frac": k1_gbs / peak,
+                     "k1_ms": k1_ms, "k1_timed_in": "a second pass of the same loop with CUDA events around K1 "
+                                                     "(%.4f ms per step there)" % probed_ms,
+                     "k1_achieved": k1_gbs, "k1_frac": k1_gbs / peak,
                      "k1_algorithmic_bytes_per_px": ALG_BYTES_K1,
                      "k1_share_of_step": k1_ms / ms_step},
         "clocks": clocks,

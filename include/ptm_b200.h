@@ -285,7 +285,14 @@ int ptmb_encode_lrgb_dev (ptmb_ctx_t *ctx, ptmb_xchg_t *xchg, const void *stack_
  *   ptmb_multi_ctx             the context of GPU i (memory helpers, ptmb_synth, ptmb_stream, ...)
  *   ptmb_multi_slab            the rows GPU i owns for an image of `height` rows
  *   ptmb_multi_encode_host     ptmb_encode_host across the GPUs: ONE host stack / ONE set of host blocks
- *                              in the caller's layout; each GPU streams its rows (synchronous)
+ *                              in the caller's layout; each GPU streams its rows (synchronous).  The rows are
+ *                              split in proportion to the host bandwidth each GPU gets when all copy at once
+ *                              (measured once, by the first call with a stack of 256 MB or more; equal slabs
+ *                              with PTM_MULTI_BALANCE=0) -- the result does not depend on the split
+ *   ptmb_multi_host_slab       the rows GPU i takes in ptmb_multi_encode_host for an image of `height` rows
+ *   ptmb_multi_set_host_weights  explicit shares (n_dev positive numbers; NULL = equal)
+ *   ptmb_multi_calibrate_h2d   measure the shares now: every GPU copies pinned host memory for `seconds`
+ *                              (<= 0: 12 ms), all at once; gbs_out (may be NULL) receives GB/s per GPU
  *   ptmb_multi_encode_lrgb_dev ptmb_encode_lrgb_dev on every GPU's resident slab (arrays of n_dev
  *                              entries); asynchronous, ptmb_multi_synchronize waits
  * This is what ptm_encode_stack / the ptm-encoder command line use when PTM_B200_DEVICES=0,1,... is set. */
@@ -295,6 +302,9 @@ void ptmb_multi_destroy (ptmb_multi_t *multi);
 int ptmb_multi_device_count (const ptmb_multi_t *multi);
 ptmb_ctx_t *ptmb_multi_ctx (ptmb_multi_t *multi, int i);
 int ptmb_multi_slab (const ptmb_multi_t *multi, size_t height, int i, size_t *row0, size_t *row1);
+int ptmb_multi_host_slab (const ptmb_multi_t *multi, size_t height, int i, size_t *row0, size_t *row1);
+int ptmb_multi_set_host_weights (ptmb_multi_t *multi, const double *weights);
+int ptmb_multi_calibrate_h2d (ptmb_multi_t *multi, double seconds, double *gbs_out);
 int ptmb_multi_set_matrix (ptmb_multi_t *multi, const float *M, unsigned n_lights);
 int ptmb_multi_set_fit_mode (ptmb_multi_t *multi, int flags);
 int ptmb_multi_synchronize (ptmb_multi_t *multi);

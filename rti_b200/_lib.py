@@ -85,6 +85,9 @@ _SIGNATURES = {
     "ptmb_multi_device_count": ([_vp], _int),
     "ptmb_multi_ctx": ([_vp, _int], _vp),
     "ptmb_multi_slab": ([_vp, _sz, _int, C.POINTER(_sz), C.POINTER(_sz)], _int),
+    "ptmb_multi_host_slab": ([_vp, _sz, _int, C.POINTER(_sz), C.POINTER(_sz)], _int),
+    "ptmb_multi_set_host_weights": ([_vp, _vp], _int),
+    "ptmb_multi_calibrate_h2d": ([_vp, C.c_double, _vp], _int),
     "ptmb_multi_set_matrix": ([_vp, _vp, C.c_uint], _int),
     "ptmb_multi_set_fit_mode": ([_vp, _int], _int),
     "ptmb_multi_synchronize": ([_vp], _int),

@@ -632,12 +632,26 @@ static int relight_common(ptmb_ctx_t *c, ptm::RelightArgs &a, bool lrgb, size_t 
     const int mode = c->relight_mode != PTMB_RELIGHT_AUTO ? c->relight_mode : env_mode;
     // AUTO: a single direction is memory bound either way and stays bit-exact; batches take the tolerance kernels
     const bool fast = mode == PTMB_RELIGHT_FAST || (mode == PTMB_RELIGHT_AUTO && n_dirs >= 4);
+    // RGB formats, tolerance form: the tensor-core kernel takes the sweep when every term scale_k * l_k(d) fits its
+    // two-term f16 split (ptm_relight_mma.cu); PTM_RELIGHT_RGB_ENGINE=ffma keeps the FFMA kernel (tuning aid)
+    float max_term = 0.f;
+    const char *rgb_engine = getenv("PTM_RELIGHT_RGB_ENGINE");   // read per call: the tests compare both engines
+    const bool rgb_mma = !(rgb_engine && !strcmp(rgb_engine, "ffma"));
+    if (fast && !lum && !lrgb && rgb_mma)
+        for (size_t i = 0; i < c->light_host.size(); ++i) {
+            const float x = fabsf(scale[i % PTMB_COEFFICIENTS] * c->light_host[i]);
+            max_term = x > max_term || x != x ? x : max_term;
+        }
     const unsigned kBatch = 960;  // light table lives in shared memory (48 bytes per direction in the packed kernels)
     for (unsigned d0 = 0; d0 < n_dirs; d0 += kBatch) {
         a.n_dirs = n_dirs - d0 < kBatch ? n_dirs - d0 : kBatch;
         a.light = c->light_dev + (size_t) d0 * PTMB_COEFFICIENTS;
         a.out = out_dev + (size_t) d0 * width * height * 3;
-        cudaError_t e = fast && !lum ? ptm::launch_relight_fast(a, lrgb, c->sm_count, c->stream) : cudaErrorNotSupported;
+        cudaError_t e = cudaErrorNotSupported;
+        if (fast && !lum && !lrgb && rgb_mma)
+            e = ptm::launch_relight_rgb_mma(a, max_term, c->sm_count, c->stream);
+        if (e == cudaErrorNotSupported && fast && !lum)
+            e = ptm::launch_relight_fast(a, lrgb, c->sm_count, c->stream);
         if (e == cudaErrorNotSupported)
             e = lum ? ptm::launch_relight_lum(a, c->sm_count, c->stream) : ptm::launch_relight(a, lrgb, c->sm_count, c->stream);
         CK(e);

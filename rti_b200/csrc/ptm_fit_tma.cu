@@ -38,12 +38,16 @@ constexpr int kTileBytes = kTilePx * 3;                  // 3072 per light
 constexpr int kWarpStageBytes = 128 * 24 + 128 * 3;      // a warp's 128 pixels: float coefficients + colour bytes
 
 // dynamic shared memory: [ring: S stages x L lights x 3072 B][2 S mbarriers][matrix: n x 32 B]
-template <int L, int S>
+// W = consumer warps: 8 (1024-pixel tiles, two CTAs per SM) or 4 (512-pixel tiles, four CTAs per SM: the same
+// bytes in flight per SM, half the finish spread -- for slabs with few tiles per CTA, see launch_fit_lrgb_tma)
+template <int L, int S, int W = kConsumerWarps>
 struct TmaSmem {
-    static constexpr size_t stage_bytes = (size_t) L * kTileBytes;
+    static constexpr int tile_px = W * 128;
+    static constexpr int tile_bytes = tile_px * 3;
+    static constexpr size_t stage_bytes = (size_t) L * tile_bytes;
     static constexpr size_t bars = (size_t) S * stage_bytes;
-    static constexpr size_t staging = bars + 2 * S * sizeof(uint64_t);        // 8 warps x (3072 + 384) B
-    static constexpr size_t matrix = staging + (size_t) kConsumerWarps * kWarpStageBytes;
+    static constexpr size_t staging = bars + 2 * S * sizeof(uint64_t);        // W warps x (3072 + 384) B
+    static constexpr size_t matrix = staging + (size_t) W * kWarpStageBytes;
     static constexpr size_t total(unsigned n_lights) { return matrix + (size_t) n_lights * 32; }
 };
 
@@ -102,8 +106,8 @@ __device__ __forceinline__ void sum_pair(const uint32_t *a, const uint32_t *b, u
 // kDebug (only instantiated in -DPTM_TUNING builds): 1 = consumers skip the arithmetic
 // (ring delivery ceiling), 2 = consumers skip the waits (arithmetic ceiling).
 // kFull: the light count is a multiple of L, so every stage is complete (no per-stage count).
-__device__ __forceinline__ unsigned tile_px_of(unsigned tile, unsigned n_tiles, unsigned tail_px) {
-    return (tail_px && tile + 1 == n_tiles) ? tail_px : (unsigned) kTilePx;
+__device__ __forceinline__ unsigned tile_px_of(unsigned tile, unsigned n_tiles, unsigned tail_px, unsigned full_px) {
+    return (tail_px && tile + 1 == n_tiles) ? tail_px : full_px;
 }
 
 __device__ __forceinline__ void st_hint(float4 *p, float4 v, uint64_t policy) {
@@ -126,10 +130,11 @@ __device__ __forceinline__ void cta_stamp(int slot) {
 #define PTM_STAMP(slot)
 #endif
 
-template <int L, int S, bool kWriteCoeffs, bool kFull, int kDebug = 0, bool kRgbIn = false>
-__global__ void __launch_bounds__(kTmaThreads, 2)
+template <int L, int S, bool kWriteCoeffs, bool kFull, int kDebug = 0, bool kRgbIn = false, int W = kConsumerWarps>
+__global__ void __launch_bounds__(W * 32 + 32, 16 / W)
 fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
-    using Smem = TmaSmem<L, S>;
+    using Smem = TmaSmem<L, S, W>;
+    constexpr int kConsumerWarps = W, kConsumers = W * 32, kTilePx = Smem::tile_px, kTileBytes = Smem::tile_bytes;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ int keys_s[2 * PTM_NCOEF];
     // Tile schedule.  The first tile of a block is blockIdx.x; with a.tile_counter the following ones are
@@ -313,7 +318,7 @@ fit_lrgb_u8_tma_kernel(FitArgs a, unsigned n_tiles, unsigned tail_px) {
                 const unsigned cra = div_magic(sum[3 * p + 2], a.magic);
                 lrgb_or_lum_finish(a.mode & kFitLum, ya, cba, cra, acc[p], out_b[3 * p], out_b[3 * p + 1], out_b[3 * p + 2]);
             }
-            if (4 * t < tile_px_of(tile, n_tiles, tail_px))   // lanes past a partial tile hold stale bytes
+            if (4 * t < tile_px_of(tile, n_tiles, tail_px, kTilePx))   // lanes past a partial tile hold stale bytes
                 ext.add4(acc);
 
             // The lane's 96 bytes of coefficients and 12 of colour go through a warp-private
@@ -369,9 +374,10 @@ extern "C" int ptmb_tuning_cta_times(unsigned long long *out, int n) {
 }
 #endif
 
-template <int L, int S, int kDebug = 0>
+template <int L, int S, int kDebug = 0, int W = kConsumerWarps>
 static cudaError_t launch_variant(const FitArgs &a, size_t n_tiles, unsigned tail_px, int sm_count, cudaStream_t st) {
-    using Smem = TmaSmem<L, S>;
+    using Smem = TmaSmem<L, S, W>;
+    constexpr int kTmaThreads = W * 32 + 32;
     static_assert(L <= 32, "one producer lane per light of a stage");
     // opt in to > 48 KB of dynamic shared memory and look up residency, once per device
     static int per_sm_cache[64][5];
@@ -383,11 +389,13 @@ static cudaError_t launch_variant(const FitArgs &a, size_t n_tiles, unsigned tai
         return cudaErrorInvalidDevice;
     const int wc = a.coeffs != nullptr;
     const bool full = a.n_lights % L == 0;
-    auto kern = wc ? (full ? fit_lrgb_u8_tma_kernel<L, S, true, true, kDebug> : fit_lrgb_u8_tma_kernel<L, S, true, false, kDebug>)
-                   : (full ? fit_lrgb_u8_tma_kernel<L, S, false, true, kDebug> : fit_lrgb_u8_tma_kernel<L, S, false, false, kDebug>);
+    auto kern = wc ? (full ? fit_lrgb_u8_tma_kernel<L, S, true, true, kDebug, false, W>
+                                : fit_lrgb_u8_tma_kernel<L, S, true, false, kDebug, false, W>)
+                   : (full ? fit_lrgb_u8_tma_kernel<L, S, false, true, kDebug, false, W>
+                           : fit_lrgb_u8_tma_kernel<L, S, false, false, kDebug, false, W>);
     int slot = wc * 2 + (full ? 1 : 0);
     if (a.mode & kFitRgbIn) {   // RGB-input stacks: the instantiation with the per-sample colour conversion
-        kern = fit_lrgb_u8_tma_kernel<L, S, true, false, 0, true>;
+        kern = fit_lrgb_u8_tma_kernel<L, S, true, false, 0, true, W>;
         slot = 4;
         if (!wc)
             return cudaErrorNotSupported;
@@ -647,40 +655,75 @@ cudaError_t launch_fit_rgb_tma(const FitArgs &a, int sm_count, cudaStream_t st, 
     return e;
 }
 
-// Launches the streaming kernel over the whole 1024-pixel tiles of the slab and returns how many
+// Launches the streaming kernel over the whole tiles of the slab (plus one partial tile) and returns how many
 // pixels it covered through *done (0 if the layout does not allow bulk copies).
+//
+// Tile size.  Tiles are handed out dynamically, so the blocks finish within about one tile of each other; with
+// 1024-pixel tiles that is ~10 us at 60 lights -- nothing in a 24 MP fit (79 tiles per CTA), 8 % of a 3 MP slab
+// (the 8-GPU shape, 9.9 tiles per CTA).  A 4-consumer-warp instantiation (512-pixel tiles, four CTAs per SM, the
+// same bytes in flight per SM) halves that spread but delivers worse: measured on B200 (profiles/r02_tile_sizes.txt)
+// 3 MP 0.1102 -> 0.1163 ms, 6 MP 0.2208 -> 0.2349, 24 MP 0.862 -> 0.898 -- 1536-byte bulk copies and twice the
+// barrier traffic cost more than the shorter tail saves.  It stays selectable (PTM_TMA_TILE=512, result-equivalent,
+// tests/test_gpu_parity.py runs every case with both) but no slab size chooses it.
+constexpr size_t kSmallSlabTilesPerCta = 0;
+
+template <int W>
+static cudaError_t launch_lrgb_tiles(const FitArgs &a, int sm_count, cudaStream_t st, size_t *done, int variant) {
+    constexpr size_t tile_px = (size_t) W * 128;
+    const size_t full_tiles = a.pixels / tile_px;
+    const unsigned rem = (unsigned) (a.pixels % tile_px);
+    // the remainder rides along as one partial tile when its byte count keeps the 16-byte granularity of bulk copies
+    const unsigned tail_px = (rem % 16 == 0) ? rem : 0;
+    const size_t n_tiles = full_tiles + (tail_px ? 1 : 0);
+    if (n_tiles == 0 || n_tiles > 0xFFFFFFFFull)
+        return cudaSuccess;
+    cudaError_t e;
+    if (W == 8) {
+        switch (variant) {
+        case 1: e = launch_variant<5, 5>(a, n_tiles, tail_px, sm_count, st); break;
+        case 2: e = launch_variant<3, 8>(a, n_tiles, tail_px, sm_count, st); break;
+        case 3: e = launch_variant<5, 4>(a, n_tiles, tail_px, sm_count, st); break;
+        case 4: e = launch_variant<4, 5>(a, n_tiles, tail_px, sm_count, st); break;
+        case 5: e = launch_variant<8, 3>(a, n_tiles, tail_px, sm_count, st); break;
+#ifdef PTM_TUNING   // delivery ceiling only: skips the arithmetic, does NOT produce results
+        case 11: e = launch_variant<6, 4, 1>(a, n_tiles, tail_px, sm_count, st); break;
+#endif
+        default: e = launch_variant<6, 4>(a, n_tiles, tail_px, sm_count, st); break;
+        }
+    } else {
+        switch (variant) {
+        case 2: e = launch_variant<3, 8, 0, W>(a, n_tiles, tail_px, sm_count, st); break;
+        case 4: e = launch_variant<4, 5, 0, W>(a, n_tiles, tail_px, sm_count, st); break;
+        default: e = launch_variant<6, 4, 0, W>(a, n_tiles, tail_px, sm_count, st); break;
+        }
+    }
+    if (e == cudaSuccess)
+        *done = full_tiles * tile_px + tail_px;
+    return e;
+}
+
 cudaError_t launch_fit_lrgb_tma(const FitArgs &a, int sm_count, cudaStream_t st, size_t *done) {
     *done = 0;
     const bool ok = a.n_lights <= 257 && ((uintptr_t) a.stack % 16 == 0) && (a.image_stride % 16 == 0) &&
                     ((uintptr_t) a.rgb % 16 == 0) && (a.coeffs == nullptr || (uintptr_t) a.coeffs % 16 == 0);
-    // whole 1024-pixel tiles, plus the remainder as one partial tile when its byte count keeps
-    // the 16-byte granularity of bulk copies (remainder % 16 == 0)
-    const size_t full_tiles = a.pixels / kTilePx;
-    const unsigned rem = (unsigned) (a.pixels % kTilePx);
-    const unsigned tail_px = (rem % 16 == 0) ? rem : 0;
-    const size_t n_tiles = full_tiles + (tail_px ? 1 : 0);
-    if (!ok || n_tiles == 0 || n_tiles > 0xFFFFFFFFull || ((a.mode & kFitRgbIn) && !a.coeffs))
+    if (!ok || ((a.mode & kFitRgbIn) && !a.coeffs))
         return cudaSuccess;
     static int variant = -1;
     if (variant < 0) {
-        const char *v = getenv("PTM_TMA_VARIANT");  // tuning aid; the default is what ships
+        const char *v = getenv("PTM_TMA_VARIANT");  // tuning aids; the defaults are what ships
         variant = v ? atoi(v) : 0;
     }
-    cudaError_t e;
-    switch (variant) {
-    case 1: e = launch_variant<5, 5>(a, n_tiles, tail_px, sm_count, st); break;
-    case 2: e = launch_variant<3, 8>(a, n_tiles, tail_px, sm_count, st); break;
-    case 3: e = launch_variant<5, 4>(a, n_tiles, tail_px, sm_count, st); break;
-    case 4: e = launch_variant<4, 5>(a, n_tiles, tail_px, sm_count, st); break;
-    case 5: e = launch_variant<8, 3>(a, n_tiles, tail_px, sm_count, st); break;
-#ifdef PTM_TUNING   // delivery ceiling only: skips the arithmetic, does NOT produce results
-    case 11: e = launch_variant<6, 4, 1>(a, n_tiles, tail_px, sm_count, st); break;
-#endif
-    default: e = launch_variant<6, 4>(a, n_tiles, tail_px, sm_count, st); break;
-    }
-    if (e == cudaSuccess)
-        *done = full_tiles * kTilePx + tail_px;
-    return e;
+    const char *t = getenv("PTM_TMA_TILE");         // read per call: the tests run every case with both tile sizes
+    const int forced_tile = t ? atoi(t) : 0;
+    const size_t big_tiles = a.pixels / kTilePx;
+    bool small = big_tiles < kSmallSlabTilesPerCta * (size_t) sm_count * 2;
+    if (forced_tile == 512)
+        small = true;
+    else if (forced_tile == 1024)
+        small = false;
+    if (a.mode & kFitRgbIn)
+        small = false;   // the RGB-input instantiation exists for the big tile only
+    return small ? launch_lrgb_tiles<4>(a, sm_count, st, done, variant) : launch_lrgb_tiles<8>(a, sm_count, st, done, variant);
 }
 
 }  // namespace ptm

@@ -88,6 +88,7 @@ struct NormalArgs {
 cudaError_t launch_normal_map(const float *coeffs, const uint8_t *bytes, const NormalArgs &a, size_t pixels,
                               float *normals, int sm_count, cudaStream_t st);
 cudaError_t launch_relight_lum(const RelightArgs &a, int sm_count, cudaStream_t st);
+cudaError_t launch_relight_rgb_mma(const RelightArgs &a, float max_term, int sm_count, cudaStream_t st);
 cudaError_t launch_fit_lsum(const FitArgs &a, bool median, int sm_count, cudaStream_t st);
 
 bool pack_mma_digits(const float *M, unsigned n_lights, std::vector<int8_t> &image, float *scale, unsigned *kpad_out);

@@ -12,7 +12,10 @@
 // host-buffer path blocks on its copies, and at 8 GPUs a device-resident fit is 0.13 ms -- issuing
 // 8 x 2 launches from one thread would leave the GPUs waiting for the host).
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -56,6 +59,26 @@ struct ptmb_multi {
     std::vector<cudaStream_t> stream;
     std::vector<Worker *> worker;
     bool peer_mailboxes = false;
+    // share of an image's rows each GPU takes in the HOST-buffer encode (equal until calibrated): the slabs
+    // arrive over PCIe, and the GPUs of one box do not all get the same host bandwidth when they copy at once
+    std::vector<double> weight;
+    bool calibrated = false;
+
+    // rows [cut(i), cut(i+1)) belong to GPU i
+    size_t cut(size_t height, int i) const {
+        if (i <= 0)
+            return 0;
+        if (i >= n)
+            return height;
+        double total = 0, upto = 0;
+        for (int j = 0; j < n; ++j) {
+            total += weight[j];
+            if (j < i)
+                upto += weight[j];
+        }
+        const size_t r = (size_t) ((double) height * (upto / total) + 0.5);
+        return std::min(r, height);
+    }
 
     // run fn(i) on every GPU's thread; returns the first failure (message moved to the caller's thread)
     int run_all(const std::function<int(int)> &fn) {
@@ -165,6 +188,7 @@ int ptmb_multi_create(const int *devices, int n_dev, ptmb_multi_t **out) {
             }
         m->device.push_back(d);
     }
+    m->weight.assign(n_dev, 1.0);
     m->ctx.assign(n_dev, nullptr);
     m->xchg.assign(n_dev, nullptr);
     m->stream.assign(n_dev, nullptr);
@@ -265,6 +289,101 @@ int ptmb_multi_slab(const ptmb_multi_t *m, size_t height, int i, size_t *row0, s
     return 0;
 }
 
+int ptmb_multi_host_slab(const ptmb_multi_t *m, size_t height, int i, size_t *row0, size_t *row1) {
+    if (!m || i < 0 || i >= m->n || !row0 || !row1)
+        return ptmb_internal_fail("ptmb_multi_host_slab", "bad argument");
+    *row0 = m->cut(height, i);
+    *row1 = m->cut(height, i + 1);
+    return 0;
+}
+
+int ptmb_multi_set_host_weights(ptmb_multi_t *m, const double *weights) {
+    if (!m)
+        return ptmb_internal_fail("ptmb_multi_set_host_weights", "NULL argument");
+    for (int i = 0; i < m->n; ++i) {
+        const double w = weights ? weights[i] : 1.0;
+        if (!(w > 0) || !(w < 1e300))
+            return ptmb_internal_fail("ptmb_multi_set_host_weights", "weights must be positive and finite");
+    }
+    for (int i = 0; i < m->n; ++i)
+        m->weight[i] = weights ? weights[i] : 1.0;
+    m->calibrated = true;   // an explicit choice is not overwritten by the automatic probe
+    return 0;
+}
+
+// Every GPU copies from its own pinned probe buffer for the same span of wall-clock time, all at once; the bytes
+// each one moved in that span are its share of the host's PCIe bandwidth under the load pattern of
+// ptmb_multi_encode_host (on the 8-GPU boxes of this pool four GPUs get 23 GB/s and four 35 GB/s).
+int ptmb_multi_calibrate_h2d(ptmb_multi_t *m, double seconds, double *gbs_out) {
+    if (!m)
+        return ptmb_internal_fail("ptmb_multi_calibrate_h2d", "NULL argument");
+    if (!(seconds > 0))
+        seconds = 0.012;
+    const size_t chunk = 8u << 20;
+    const int n = m->n;
+    std::vector<double> rate(n, 0.0);
+    std::atomic<int> ready(0);
+    const int rc = m->run_all([&, m](int i) -> int {
+        void *host = nullptr, *dev = nullptr;
+        cudaStream_t st = m->stream[i];
+        cudaError_t e = cudaHostAlloc(&host, 2 * chunk, cudaHostAllocPortable);
+        if (e == cudaSuccess)
+            e = cudaMalloc(&dev, 2 * chunk);
+        if (e == cudaSuccess) {
+            std::memset(host, 0x5a, 2 * chunk);
+            e = cudaMemcpyAsync(dev, host, 2 * chunk, cudaMemcpyHostToDevice, st);   // first touch / mapping
+        }
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(st);
+        // all GPUs start together, also when one of them failed to set up
+        ready.fetch_add(1);
+        while (ready.load() < n)
+            std::this_thread::yield();
+        size_t moved = 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        double dt = 0;
+        if (e == cudaSuccess) {
+            // two chunk copies in flight: the link never idles while the host thread turns around
+            cudaEvent_t ev[2];
+            cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+            int k = 0;
+            cudaMemcpyAsync(dev, host, chunk, cudaMemcpyHostToDevice, st);
+            cudaEventRecord(ev[0], st);
+            for (;;) {
+                k ^= 1;
+                cudaMemcpyAsync((char *) dev + k * chunk, (char *) host + k * chunk, chunk, cudaMemcpyHostToDevice, st);
+                cudaEventRecord(ev[k], st);
+                e = cudaEventSynchronize(ev[k ^ 1]);
+                moved += chunk;
+                dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                if (e != cudaSuccess || dt >= seconds)
+                    break;
+            }
+            cudaStreamSynchronize(st);
+            cudaEventDestroy(ev[0]);
+            cudaEventDestroy(ev[1]);
+        }
+        if (dev)
+            cudaFree(dev);
+        if (host)
+            cudaFreeHost(host);
+        if (e != cudaSuccess)
+            return ptmb_internal_fail("ptmb_multi_calibrate_h2d", cudaGetErrorString(e));
+        rate[i] = (double) moved / dt;
+        return 0;
+    });
+    if (rc)
+        return rc;
+    for (int i = 0; i < n; ++i) {
+        m->weight[i] = rate[i];
+        if (gbs_out)
+            gbs_out[i] = rate[i] / 1e9;
+    }
+    m->calibrated = true;
+    return 0;
+}
+
 int ptmb_multi_set_matrix(ptmb_multi_t *m, const float *M, unsigned n_lights) {
     if (!m)
         return ptmb_internal_fail("ptmb_multi_set_matrix", "NULL argument");
@@ -303,9 +422,17 @@ int ptmb_multi_encode_host(ptmb_multi_t *m, const void *stack_host, int sample_t
                                 blocks_host, coeffs_host, sb_host);
     const size_t image_bytes = width * height * 3 * ss;
     const size_t plane_floats = width * height * PTMB_COEFFICIENTS;
+    // the first large host encode measures every GPU's share of the host bandwidth once (PTM_MULTI_BALANCE=0:
+    // equal slabs); results do not depend on the split (tests/test_gpu_multi.py)
+    if (!m->calibrated && image_bytes * n_lights >= ((size_t) 256 << 20)) {
+        const char *env = getenv("PTM_MULTI_BALANCE");
+        if (!(env && env[0] == '0') && ptmb_multi_calibrate_h2d(m, 0.012, nullptr))
+            return 1;
+        m->calibrated = true;
+    }
     std::vector<ptmb_scale_bias_t> sb(m->n);
     const int rc = m->run_all([&, m](int i) -> int {
-        const size_t r0 = (size_t) i * height / (size_t) m->n, r1 = (size_t) (i + 1) * height / (size_t) m->n;
+        const size_t r0 = m->cut(height, i), r1 = m->cut(height, i + 1);
         const size_t rows = r1 - r0, px0 = r0 * width;
         ptmb_ctx_t *c = m->ctx[i];
         int32_t *keys = ptmb_internal_keys(c);
@@ -333,7 +460,7 @@ int ptmb_multi_encode_host(ptmb_multi_t *m, const void *stack_host, int sample_t
         return rc;
     // every GPU derived scale / bias from the same merged keys; report those of the first non-empty slab
     for (int i = 0; i < m->n; ++i) {
-        const size_t r0 = (size_t) i * height / (size_t) m->n, r1 = (size_t) (i + 1) * height / (size_t) m->n;
+        const size_t r0 = m->cut(height, i), r1 = m->cut(height, i + 1);
         if (r1 > r0) {
             *sb_host = sb[i];
             break;

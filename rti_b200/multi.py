@@ -73,6 +73,26 @@ class MultiGpu:
         _lib.check(self._lib.ptmb_multi_slab(self._h, height, i, C.byref(r0), C.byref(r1)))
         return r0.value, r1.value
 
+    def host_slab(self, height, i):
+        """Rows GPU i takes in encode_host (bandwidth-proportional once calibrated)."""
+        r0, r1 = C.c_size_t(0), C.c_size_t(0)
+        _lib.check(self._lib.ptmb_multi_host_slab(self._h, height, i, C.byref(r0), C.byref(r1)))
+        return r0.value, r1.value
+
+    def set_host_weights(self, weights=None):
+        if weights is None:
+            _lib.check(self._lib.ptmb_multi_set_host_weights(self._h, None))
+        else:
+            assert len(weights) == self.n
+            arr = (C.c_double * self.n)(*[float(w) for w in weights])
+            _lib.check(self._lib.ptmb_multi_set_host_weights(self._h, arr))
+
+    def calibrate_h2d(self, seconds=0.0):
+        """Concurrent pinned host -> device probe on every GPU; returns GB/s per GPU and adopts them as weights."""
+        out = (C.c_double * self.n)()
+        _lib.check(self._lib.ptmb_multi_calibrate_h2d(self._h, float(seconds), out))
+        return list(out)
+
     def set_matrix(self, M):
         M = np.ascontiguousarray(M, dtype=np.float32)
         self._M = M
@@ -163,6 +183,9 @@ def bench_multi(args, B):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
     sampler = B.ClockSampler(B.physical_gpu_index(0))
     sampler.start()
+    # one untimed encode lines the GPUs up on the device (every K2 waits for all peers' keys) before the start
+    # events: the host threads do not release their first launches at the same instant
+    mg.encode_lrgb_dev(a)
     for i in range(n):
         with torch.cuda.device(mg.devices[i]):
             ev[i][0].record(streams[i])
@@ -197,6 +220,12 @@ def bench_multi(args, B):
         for i, (r0, r1) in enumerate(slabs):
             host_stack[:, r0:r1].copy_(stacks[i])
         out = [torch.empty((H, W, 6), dtype=torch.uint8).pin_memory(), torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()]
+        if os.environ.get("PTM_E2E_BALANCE", "1") == "1":
+            rates = mg.calibrate_h2d()                     # rows follow each GPU's share of the host bandwidth
+        else:
+            rates = None
+            mg.set_host_weights(None)
+        host_rows = [mg.host_slab(H, i) for i in range(n)]
         mg.encode_host(host_stack, M, planes=1, out=out)
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
@@ -207,6 +236,7 @@ def bench_multi(args, B):
         e2e = {"value": W * H / e2e_s / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
                "h2d_bytes_per_step": int(host_stack.numel()), "d2h_bytes_per_step": int(out[0].numel() + out[1].numel()),
                "h2d_gbs": host_stack.numel() / e2e_s / 1e9, "identical_to_single_gpu": bool(ident),
+               "h2d_share_gbs_per_gpu": rates, "rows_per_gpu": [r1 - r0 for r0, r1 in host_rows],
                "note": "whole-job bytes; one pinned host stack -> ptmb_multi_encode_host -> pinned host blocks"}
     peak, peak_src = B.measured_peak()
     path_gbs = B.ALG_BYTES_PATH * W * H / (ms_step * 1e-3) / 1e9 / n

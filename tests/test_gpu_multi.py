@@ -122,6 +122,34 @@ def test_multi_encode_host_equals_single_gpu(oracle, planes, mode):
         mg.close()
 
 
+def test_multi_encode_host_unequal_slabs(oracle):
+    """Bandwidth-proportional slabs (ptmb_multi_calibrate_h2d / ptmb_multi_set_host_weights): any split of the rows
+    gives the single-GPU bytes, including a split that leaves a GPU without rows."""
+    from rti_b200.multi import MultiGpu
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    W, H = 128, 301
+    L, M, stack, want = _single_gpu_reference(oracle, W, H, 1, 0xD159, 0)
+    mg = MultiGpu(None)
+    rates = mg.calibrate_h2d(0.005)
+    assert len(rates) == n and all(r > 0.5 for r in rates), rates      # GB/s
+    print("concurrent pinned H2D, GB/s per GPU:", ["%.1f" % r for r in rates])
+    for weights in (None, [1.0 + 2.0 * (i % 2) for i in range(n)], [1e-9] + [1.0] * (n - 1), "calibrated"):
+        if weights == "calibrated":
+            mg.calibrate_h2d(0.005)
+        else:
+            mg.set_host_weights(weights)
+        cuts = [mg.host_slab(H, i) for i in range(n)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == H and all(cuts[i][1] == cuts[i + 1][0] for i in range(n - 1)), cuts
+        got = mg.encode_host(stack, M, planes=1, want_coeffs=True)
+        for a, b in zip(got["blocks"], want["blocks"]):
+            np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(got["coeffs"], want["coeffs"])
+        np.testing.assert_array_equal(got["bias"], want["bias"])
+    mg.close()
+
+
 def test_multi_more_gpus_than_rows(oracle):
     """Slabs may be empty (2 rows over up to 8 GPUs): empty GPUs still take part in the key exchange."""
     from rti_b200.multi import MultiGpu

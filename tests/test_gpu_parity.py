@@ -115,6 +115,41 @@ def test_lrgb_encode_vs_oracle(ctx, oracle, dome1, M60, W, H, seed):
         assert_byte_parity(got["coef"], want["coef"], got["bias"], want["bias"], "LRGB coefficient bytes %dx%d" % (W, H))
 
 
+@pytest.mark.parametrize("W,H,seed", [(256, 192, 5), (1040, 37, 8), (2000, 752, 9)])
+def test_lrgb_ring_tile_sizes_give_the_same_bytes(ctx, oracle, dome1, M60, W, H, seed, monkeypatch):
+    """K1's ring kernel exists with 1024-pixel tiles (8 consumer warps, 2 CTAs / SM) and with 512-pixel tiles
+    (4 consumer warps, 4 CTAs / SM; chosen for slabs with few tiles per CTA).  Both must give the oracle's result,
+    and each other's bit for bit (same per-pixel arithmetic, extrema merged with integer max), for whole tiles,
+    a partial last tile (1040 x 37 = 75 x 512 + 80 = 37 x 1024 + 592) and the plain / fused entry points."""
+    from rti_b200.device import NCOEF
+    stack = oracle.synth_stack(seed, 0, W, H, dome1)
+    want = oracle.encode_lrgb(stack, M60)
+    P = W * H
+    res = {}
+    for tile in ("512", "1024"):
+        monkeypatch.setenv("PTM_TMA_TILE", tile)
+        got = gpu_encode_lrgb(ctx, stack, M60)
+        assert coeff_error(got["coeffs"], want["coeffs"], M60, stack[..., 0], lrgb=True) <= 1e-5
+        np.testing.assert_array_equal(got["rgb"], want["rgb"])
+        assert_byte_parity(got["coef"], want["coef"], got["bias"], want["bias"], "tile %s, %dx%d" % (tile, W, H))
+        # the fused two-launch encode on the same tile size
+        d_stack = dev(stack)
+        coeffs = torch.empty((P, NCOEF), dtype=torch.float32, device="cuda")
+        rgb = torch.zeros((P, 3), dtype=torch.uint8, device="cuda")
+        coef = torch.zeros((P, NCOEF), dtype=torch.uint8, device="cuda")
+        sb = torch.empty(12, dtype=torch.int32, device="cuda")
+        for _ in range(2):
+            ctx.encode_lrgb_dev(d_stack, P * 3, P, coeffs, rgb, coef, sb)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(coeffs.cpu().numpy().reshape(H, W, NCOEF), got["coeffs"])
+        np.testing.assert_array_equal(coef.cpu().numpy().reshape(H, W, NCOEF), got["coef"])
+        np.testing.assert_array_equal(rgb.cpu().numpy().reshape(H, W, 3), got["rgb"])
+        res[tile] = got
+    monkeypatch.delenv("PTM_TMA_TILE")
+    for k in ("coeffs", "coef", "rgb", "scale", "bias"):
+        np.testing.assert_array_equal(res["512"][k], res["1024"][k])
+
+
 @pytest.mark.parametrize("engine", ["ffma", "mma"])
 def test_plain_and_fused_entry_points_interleave(ctx, oracle, dome1, M60, engine):
     """The dynamic tile schedule keeps a device counter at 0 between launches; the plain fit (cleared by a

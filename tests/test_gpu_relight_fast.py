@@ -67,6 +67,49 @@ def test_rgb_sweep_within_one(ctx, oracle, dome1, M60):
     check_within_one(got, want, "RGB-format sweep")
 
 
+def test_rgb_sweep_on_tensor_cores_within_one(ctx, oracle, dome1, M60, monkeypatch):
+    """RGB-format sweeps with a width that is a multiple of 16 run on the tensor cores (relight_rgb_mma_kernel,
+    rti_b200/csrc/ptm_relight_mma.cu: f16 operands, two-term split of scale * l).  Every byte within 1 of the oracle;
+    2240 pixels = 17.5 warp units (a partial last unit), 94 directions = 5.9 direction tiles (a partial last tile);
+    the FFMA tolerance kernel on the same input for comparison."""
+    W, H = 64, 35
+    stack = oracle.synth_stack(29, 1, W, H, dome1)
+    enc = oracle.encode_rgb(stack, M60)
+    scale = oracle.header_roundtrip(enc["scale"])
+    uv = np.concatenate([ring(90), [[0, 0], [1, 0], [0, -1], [1, 1]]]).astype(np.float32)
+    planes = [dev(enc["coef"][c]) for c in range(3)]
+    want = np.stack([oracle.relight_rgb(enc["coef"], scale, enc["bias"], float(u), float(v)) for u, v in uv])
+    res = {}
+    for engine in ("mma", "ffma"):
+        monkeypatch.setenv("PTM_RELIGHT_RGB_ENGINE", engine)
+        out = torch.full((len(uv), H, W, 3), 7, dtype=torch.uint8, device="cuda")
+        ctx.relight_rgb(planes[0], planes[1], planes[2], W, H, scale, enc["bias"], uv, out)
+        res[engine] = out.cpu().numpy()
+        check_within_one(res[engine], want, "RGB-format sweep, %s engine" % engine)
+    monkeypatch.delenv("PTM_RELIGHT_RGB_ENGINE")
+    assert np.abs(res["mma"].astype(int) - res["ffma"].astype(int)).max() <= 1
+
+
+def test_rgb_tensor_core_random_blocks_and_chunk_shapes(ctx, oracle, monkeypatch):
+    """Uniformly random blocks (every byte value in every coefficient), biases at both ends of 0..255 and scales up
+    to the largest the f16 split takes (|scale * l| <= 64): the polynomial leaves 0..255 both ways and must saturate
+    like the reference's CLIP.  A scale above the limit is served by the FFMA kernel (same bar)."""
+    rng = np.random.default_rng(78)
+    W, H = 80, 13
+    uv = np.concatenate([ring(16, 0.9), [[0, 0], [1.0, -1.0], [0.999, 0.999]]]).astype(np.float32)
+    coef = rng.integers(0, 256, (3, H, W, 6), dtype=np.uint8)
+    for scale, bias in (([0.9, 1.1, 0.7, 1.3, 0.8, 1.0], [120, 131, 117, 125, 140, 10]),
+                        ([60.0, 33.0, 0.01, 1e-4, 64.0, 2.5], [0, 255, 128, 1, 254, 64]),
+                        ([2.0, 2.0, 2.0, 2.0, 2.0, 2.0], [-1000, 1024, 0, 255, 300, -5]),
+                        ([65.0, 1.0, 1.0, 1.0, 1.0, 1.0], [128, 128, 128, 128, 128, 128])):
+        scale = np.asarray(scale, np.float32)
+        bias = np.asarray(bias, np.int32)
+        want = np.stack([oracle.relight_rgb(coef, scale, bias, float(u), float(v)) for u, v in uv])
+        out = torch.empty((len(uv), H, W, 3), dtype=torch.uint8, device="cuda")
+        ctx.relight_rgb(dev(coef[0]), dev(coef[1]), dev(coef[2]), W, H, scale, bias, uv, out)
+        check_within_one(out.cpu().numpy(), want, "RGB random blocks, scale %g" % scale[0])
+
+
 @pytest.mark.parametrize("fmt", ["lrgb", "rgb"])
 def test_random_blocks_and_out_of_range_pixels(ctx, oracle, fmt):
     """Uniformly random blocks with scales / biases that push the polynomial far outside 0..255 in both
@@ -118,6 +161,44 @@ def test_auto_mode_is_exact_for_single_directions(oracle, dome1, M60):
     np.testing.assert_array_equal(out.cpu().numpy()[0],
                                   oracle.relight_lrgb(enc["coef"], enc["rgb"], scale, enc["bias"], 0.3, -0.2))
     c.close()
+
+
+def test_full_size_rgb_sweep_tensor_cores_vs_exact(ctx, oracle, dome1, M60):
+    """The RGB-format half of BASELINE.json configs[4] at full size: the tensor-core kernel against the bit-exact
+    kernel over every byte of 24 sampled directions of a 24 MP x 360 sweep."""
+    from rti_b200.device import U8, Context, light_q14
+    from rti_b200.encoder import PtmEncoder
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs about 40 GB of free HBM")
+    W, H = 6000, 4000
+    P = W * H
+    stack = torch.empty((60, H, W, 3), dtype=torch.uint8, device="cuda")
+    ctx.synth(0x5EED0001, 1, U8, 0, P, light_q14(dome1), stack, P * 3)
+    enc = PtmEncoder(W, H, M60, planes=3)
+    enc.encode(stack)
+    torch.cuda.synchronize()
+    del stack
+    scale, bias = enc.scale_bias()
+    scale = oracle.header_roundtrip(scale)
+    uv = ring(360)
+    cb = enc.coef_bytes
+    out = torch.empty((360, H, W, 3), dtype=torch.uint8, device="cuda")
+    ctx.relight_rgb(cb[0], cb[1], cb[2], W, H, scale, bias, uv, out)
+    exact = Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    exact.set_relight_mode("exact")
+    one = torch.empty((1, H, W, 3), dtype=torch.uint8, device="cuda")
+    differing, worst = 0, 0
+    for d in range(0, 360, 15):
+        exact.relight_rgb(cb[0], cb[1], cb[2], W, H, scale, bias, uv[d:d + 1], one)
+        delta = (out[d].to(torch.int16) - one[0].to(torch.int16)).abs()
+        worst = max(worst, int(delta.max()))
+        differing += int((delta != 0).sum())
+    print("RGB format, 24 MP x 24 directions: %d of %d bytes differ, max |delta| %d (scale %s)"
+          % (differing, 24 * P * 3, worst, scale))
+    assert worst <= 1
+    assert differing <= 24 * P * 3 // 200
+    exact.close()
 
 
 def test_full_size_sweep_fast_vs_exact(ctx, oracle, dome1, M60):

@@ -1,0 +1,13 @@
+#!/bin/bash
+# round 2, GPU call 10: tensor-core RGB relight kernel (parity, chunk shapes, FFMA kernel beside it, ncu capture)
+O=gpurun_out
+mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_relight_fast.py -m gpu -x -q -s > $O/r02j_pytest.log 2>&1; echo "pytest rc=$?" >> $O/r02j_pytest.log
+{
+for nc in 16 24 32; do PTM_RELIGHT_MMA_CHUNKS=$nc python tools/relight_once.py 360 rgb fast | sed "s/^/mma chunks $nc: /"; done
+PTM_RELIGHT_RGB_ENGINE=ffma python tools/relight_once.py 360 rgb fast | sed "s/^/ffma: /"
+python tools/relight_once.py 360 lrgb fast
+} > $O/r02j_relight.txt 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:relight_rgb_mma -c 1 -f -o $O/r02j_prof_relight_rgb_mma \
+    python tools/relight_once.py 360 rgb fast > $O/r02j_ncu.log 2>&1
+tail -25 $O/r02j_pytest.log; cat $O/r02j_relight.txt
