@@ -4,7 +4,7 @@ O=gpurun_out
 mkdir -p $O
 timeout 900 python -m pytest tests/test_gpu_relight_fast.py -m gpu -x -q -s > $O/r02j_pytest.log 2>&1; echo "pytest rc=$?" >> $O/r02j_pytest.log
 {
-for nc in 16 24 32; do PTM_RELIGHT_MMA_CHUNKS=$nc python tools/relight_once.py 360 rgb fast | sed "s/^/mma chunks $nc: /"; done
+for sh in 0 1 2 3 4 5 6 7; do PTM_RELIGHT_MMA_SHAPE=$sh python tools/relight_once.py 360 rgb fast | sed "s/^/mma shape $sh: /"; done
 PTM_RELIGHT_RGB_ENGINE=ffma python tools/relight_once.py 360 rgb fast | sed "s/^/ffma: /"
 python tools/relight_once.py 360 lrgb fast
 } > $O/r02j_relight.txt 2>&1
