@@ -770,6 +770,11 @@ static void encode_scratch_release(ptmb_ctx *c) {
     if (s.fitted)
         cudaEventDestroy(s.fitted);
     s.fitted = nullptr;
+    if (s.copy_t0)
+        cudaEventDestroy(s.copy_t0);
+    if (s.copy_t1)
+        cudaEventDestroy(s.copy_t1);
+    s.copy_t0 = s.copy_t1 = nullptr;
     s.early_rgb = s.early_rgb_done = nullptr;
     s.stage_bytes = s.coeff_floats = s.out_bytes = 0;
     s.valid = false;
@@ -823,6 +828,8 @@ int ptmb_internal_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, size_t 
     s.early_rgb_done = nullptr;
     if (!s.copy) {
         CK(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&s.copy_t0));
+        CK(cudaEventCreate(&s.copy_t1));
         for (int i = 0; i < 2; ++i) {
             CK(cudaEventCreateWithFlags(&s.copied[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&s.consumed[i], cudaEventDisableTiming));
@@ -871,6 +878,7 @@ int ptmb_internal_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, size_t 
         }
     }
     int buf = 0;
+    CK(cudaEventRecord(s.copy_t0, s.copy));
     for (size_t row = 0; row < height; row += slab_rows, buf ^= 1) {
         const size_t rows = height - row < slab_rows ? height - row : slab_rows;
         const size_t px0 = row * width, npx = rows * width;
@@ -908,6 +916,7 @@ int ptmb_internal_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, size_t 
                 CK(cudaMemcpyAsync(early + px0 * 3, rgb_dev + px0 * 3, npx * 3, cudaMemcpyDeviceToHost, s.back));
         }
     }
+    CK(cudaEventRecord(s.copy_t1, s.copy));
     if (early) {
         CK(cudaEventRecord(s.fitted, s.back));
         s.early_rgb_done = early;
@@ -917,6 +926,17 @@ int ptmb_internal_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, size_t 
                            c->stream));
     s.valid = true;
     return 0;
+}
+
+// Milliseconds the input copies of the last ptmb_encode_host_fit took on the copy stream (first to last byte),
+// valid once that work has completed; < 0 when unknown.  ptm_multi.cu balances its row slabs with it.
+extern "C" float ptmb_internal_last_copy_ms(ptmb_ctx_t *c) {
+    float ms = -1.f;
+    if (!c || !c->enc.copy_t0 || cudaEventElapsedTime(&ms, c->enc.copy_t0, c->enc.copy_t1) != cudaSuccess) {
+        cudaGetLastError();
+        return -1.f;
+    }
+    return ms;
 }
 
 int ptmb_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, int sample_type, size_t width, size_t height,

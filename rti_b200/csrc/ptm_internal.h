@@ -16,6 +16,7 @@ struct EncodeScratch {
     cudaStream_t copy = nullptr;
     cudaStream_t back = nullptr;          // device -> host copies that overlap the fit (early RGB block)
     cudaEvent_t fitted = nullptr;
+    cudaEvent_t copy_t0 = nullptr, copy_t1 = nullptr;   // first / last host -> device copy of the last fit (timed)
     uint8_t *early_rgb = nullptr;         // host destination set by ptmb_encode_host_early_rgb, consumed by the next fit
     uint8_t *early_rgb_done = nullptr;    // what the last fit already copied back
     cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};

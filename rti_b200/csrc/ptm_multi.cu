@@ -30,6 +30,7 @@
 extern "C" int ptmb_internal_fail(const char *what, const char *detail);
 extern "C" int32_t *ptmb_internal_keys(ptmb_ctx_t *c);
 extern "C" void ptmb_internal_set_host_threads(ptmb_ctx_t *c, int n);
+extern "C" float ptmb_internal_last_copy_ms(ptmb_ctx_t *c);
 extern "C" int ptmb_internal_encode_host_fit(ptmb_ctx_t *c, const void *stack_host, size_t host_image_bytes,
                                              int sample_type, size_t width, size_t height, unsigned n_lights,
                                              const float *M, int format_planes, int32_t *keys_dev);
@@ -63,6 +64,8 @@ struct ptmb_multi {
     // arrive over PCIe, and the GPUs of one box do not all get the same host bandwidth when they copy at once
     std::vector<double> weight;
     bool calibrated = false;
+    bool explicit_weights = false;   // set by ptmb_multi_set_host_weights: never adjusted automatically
+    int refinements = 0;             // automatic adjustments made from the copy times of real encodes
 
     // rows [cut(i), cut(i+1)) belong to GPU i
     size_t cut(size_t height, int i) const {
@@ -308,6 +311,8 @@ int ptmb_multi_set_host_weights(ptmb_multi_t *m, const double *weights) {
     for (int i = 0; i < m->n; ++i)
         m->weight[i] = weights ? weights[i] : 1.0;
     m->calibrated = true;   // an explicit choice is not overwritten by the automatic probe
+    m->explicit_weights = weights != nullptr;
+    m->refinements = 0;
     return 0;
 }
 
@@ -381,6 +386,8 @@ int ptmb_multi_calibrate_h2d(ptmb_multi_t *m, double seconds, double *gbs_out) {
             gbs_out[i] = rate[i] / 1e9;
     }
     m->calibrated = true;
+    m->explicit_weights = false;
+    m->refinements = 0;
     return 0;
 }
 
@@ -431,6 +438,7 @@ int ptmb_multi_encode_host(ptmb_multi_t *m, const void *stack_host, int sample_t
         m->calibrated = true;
     }
     std::vector<ptmb_scale_bias_t> sb(m->n);
+    std::vector<double> copy_ms(m->n, -1.0);
     const int rc = m->run_all([&, m](int i) -> int {
         const size_t r0 = m->cut(height, i), r1 = m->cut(height, i + 1);
         const size_t rows = r1 - r0, px0 = r0 * width;
@@ -453,11 +461,35 @@ int ptmb_multi_encode_host(ptmb_multi_t *m, const void *stack_host, int sample_t
             return 1;
         if (ptmb_xchg_allreduce_max(c, m->xchg[i], keys))
             return 1;
-        return ptmb_internal_encode_host_finish(c, nullptr, blk, coeffs_host ? coeffs_host + px0 * PTMB_COEFFICIENTS : nullptr,
-                                                plane_floats, &sb[i]);
+        if (ptmb_internal_encode_host_finish(c, nullptr, blk, coeffs_host ? coeffs_host + px0 * PTMB_COEFFICIENTS : nullptr,
+                                             plane_floats, &sb[i]))
+            return 1;
+        copy_ms[i] = ptmb_internal_last_copy_ms(c);   // on the GPU's own thread (its device is current)
+        return 0;
     });
     if (rc)
         return rc;
+    // The probe's small copies do not load the links exactly like slab-sized ones: while the split was chosen
+    // automatically, the copy times of this encode (first to last input byte per GPU) correct it for the next
+    // one -- rows follow rows_i / t_i when the GPUs finished more than 4 % apart (at most 3 corrections).
+    if (m->calibrated && !m->explicit_weights && m->refinements < 3 && image_bytes * n_lights >= ((size_t) 256 << 20)) {
+        const std::vector<double> &ms = copy_ms;
+        double lo = 1e300, hi = 0;
+        bool ok = true;
+        for (int i = 0; i < m->n && ok; ++i) {
+            const size_t rows = m->cut(height, i + 1) - m->cut(height, i);
+            ok = rows > 0 && ms[i] > 0;
+            lo = std::min(lo, ms[i]);
+            hi = std::max(hi, ms[i]);
+        }
+        if (ok && hi > 1.04 * lo) {
+            std::vector<double> w(m->n);
+            for (int i = 0; i < m->n; ++i)
+                w[i] = (double) (m->cut(height, i + 1) - m->cut(height, i)) / ms[i];
+            m->weight = w;
+            ++m->refinements;
+        }
+    }
     // every GPU derived scale / bias from the same merged keys; report those of the first non-empty slab
     for (int i = 0; i < m->n; ++i) {
         const size_t r0 = m->cut(height, i), r1 = m->cut(height, i + 1);

@@ -97,3 +97,21 @@ def test_mma_digit_packing_reproduces_the_dot_product_exactly(oracle, dome1, M60
     bad[2, 5] = np.inf
     assert lib.ptmb_mma_pack_digits(bad.ctypes.data, 60, image.ctypes.data, image.nbytes, scale.ctypes.data,
                                     C.byref(kpad)) != 0
+
+
+def test_weighted_row_cuts_cover_the_image():
+    """Bandwidth-proportional row slabs of the host-buffer legs (bench.weighted_cuts, same formula as
+    ptm_multi.cu:cut): boundaries are monotone, cover every row once, follow the weights, and equal weights
+    reproduce the floor(i*H/n) slabs up to rounding."""
+    import bench
+    rng = np.random.default_rng(5)
+    for H in (1, 2, 7, 500, 4000, 5792):
+        for n in (1, 2, 3, 8):
+            for w in ([1.0] * n, list(rng.uniform(0.2, 5.0, n)), [23.3] * (n // 2) + [35.3] * (n - n // 2)):
+                cuts = bench.weighted_cuts(H, w)
+                assert len(cuts) == n + 1 and cuts[0] == 0 and cuts[-1] == H
+                assert all(a <= b for a, b in zip(cuts, cuts[1:]))
+                tot = sum(w)
+                for i in range(n):
+                    assert abs((cuts[i + 1] - cuts[i]) - H * w[i] / tot) <= 1.0
+    assert bench.weighted_cuts(4000, [23.3] * 4 + [35.3] * 4) == [0, 398, 795, 1193, 1590, 2193, 2795, 3398, 4000]
