@@ -257,7 +257,8 @@ void HostState::release() {
     if (pipe_ok)
         pipe.destroy();
     pipe_ok = false;
-    for (int i = 0; i < 4; ++i) {
+    spec_valid = false;
+    for (int i = 0; i < 6; ++i) {
         cudaFree(scratch[i]);
         scratch[i] = nullptr;
         scratch_cap[i] = 0;

@@ -99,8 +99,13 @@ struct HostState {
     bool served_avg = false;
     bool valid = false;
     // scratch
-    void *scratch[4] = {};
-    size_t scratch_cap[4] = {};
+    void *scratch[6] = {};
+    size_t scratch_cap[6] = {};
+    // what ptm_lrgb_finish left on the device for the ptm_scale_coefficients that normally follows (ptm_api_host.cu):
+    // its float results (scratch[4]) and their quantised bytes + scale / bias (scratch[5]), for host buffer spec_host
+    const float *spec_host = nullptr;
+    size_t spec_pixels = 0;
+    bool spec_valid = false;
     cudaError_t reserve(int i, size_t bytes);
     void release();
 };

@@ -122,3 +122,58 @@ def test_pinned_and_pageable_buffers_agree(oracle, dome1):
     rows = [0, 299, 599]
     np.testing.assert_allclose(f1.reshape(H, W, 6)[rows], oracle.fit_u8(np.ascontiguousarray(stack[:, rows]), M),
                                rtol=0, atol=2e-3)
+
+
+def test_scale_after_finish_is_verified_not_trusted(oracle, dome1):
+    """With pinned (registered) caller buffers ptm_lrgb_finish keeps its float results on the device and quantises them
+    ahead of the ptm_scale_coefficients that normally follows; that call then only verifies, bit for bit, that the host
+    buffer still holds those floats while the bytes already travel back (rti_b200/csrc/ptm_api_host.cu).  Unchanged
+    floats must give the ordinary path's bytes; a caller that CHANGES a coefficient between the two calls (the
+    reference's encoder is free to) must get the bytes of the changed floats -- never the speculative ones."""
+    import torch
+    from rti_b200 import ptmlib as P
+    W, H = 256, 130                                                  # even pixel count: the compare covers every byte
+    M = P.ptm_svd(dome1)
+    info = P.image_info(W, H, 60)
+    stack = np.ascontiguousarray(oracle.synth_stack(0xAB8, 0, W, H, dome1))
+
+    def sequence(pinned, poke):
+        hdr = P.ptm_alloc_header("PTM_FORMAT_LRGB", W, H)
+        hold = []
+
+        def buf(a):
+            if not pinned:
+                return a
+            t = torch.from_numpy(a).pin_memory()
+            hold.append(t)
+            return t.numpy()
+
+        blocks = [buf(b) for b in P.ptm_alloc_blocks(hdr)]
+        coeffs = buf(np.zeros((W * H, 6), np.float32))
+        M32 = np.ascontiguousarray(M, dtype=np.float32)
+        L = P.lib()
+        import ctypes as C
+        L.ptm_fit_poly_jsample(C.byref(info), stack.ctypes.data, 3, M32.ctypes.data, coeffs.ctypes.data)
+        L.ptm_cbcr_avg(C.byref(info), stack.ctypes.data, blocks[1].ctypes.data)
+        L.ptm_lrgb_finish(C.byref(info), blocks[1].ctypes.data, coeffs.ctypes.data)
+        if poke == "extremum":
+            coeffs[12345, 2] = 1.0e6          # moves the global maximum of c2: every byte of that coefficient changes
+        elif poke == "last":
+            coeffs[-1, 5] += 0.75             # the very last float of the plane
+        L.ptm_scale_coefficients(C.byref(hdr), coeffs.ctypes.data, P._block_ptrs(blocks))
+        return (np.array(blocks[0], copy=True), np.array(blocks[1], copy=True), np.array(hdr.scale, np.float32),
+                np.array(hdr.bias, np.int32), np.array(coeffs, copy=True))
+
+    for poke in (None, "extremum", "last"):
+        want = sequence(False, poke)           # pageable buffers: the ordinary path
+        got = sequence(True, poke)             # pinned buffers: speculation + verification
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a, b)
+    plain = sequence(True, None)
+    poked = sequence(True, "extremum")
+    assert not np.array_equal(plain[0], poked[0]) and poked[2][2] > 100 * plain[2][2]
+    # and the whole sequence against the oracle
+    ref = oracle.encode_lrgb(stack, M)
+    np.testing.assert_array_equal(plain[1].reshape(H, W, 3), ref["rgb"])
+    d = np.abs(plain[0].reshape(H, W, 6).astype(int) - ref["coef"].astype(int))
+    assert d.max() <= 1 and (d != 0).mean() < 0.01
