@@ -758,6 +758,9 @@ def run_b200(args):
                                                % (stack.numel() / 1e6),
                    "driver": "one process per GPU (torchrun)" if world > 1 else "one process",
                    "stack_stable": stack_stable,
+                   "timed_region": "K back-to-back encodes between two CUDA events, nothing else enqueued" +
+                                   ("; one untimed encode after the barrier lines the ranks up on the device first"
+                                    if world > 1 else ""),
                    "exchange": {"none": "none", "nccl": "int32 MAX all-reduce of 12 keys (NCCL)",
                                 "p2p": "12 int32 keys written into every peer's mailbox over NVLink by K1's last block, picked up in K2's prologue"}
                                [enc.exchange_kind]},
