@@ -81,14 +81,14 @@ def measured_peak():
 
 
 def kernel_sources_sha256():
-    """Hash of the CUDA sources the shipped library was built from; profiles/traffic.json records the hash of the
-    sources its ncu capture was taken with, so a stale capture is reported as such instead of being quoted."""
+    """Hash of the sources of the two kernels profiles/traffic.json speaks about (K1 = ptm_fit_tma.cu, K2 =
+    ptm_quantise.cu, and the headers they include); traffic.json records the hash its ncu capture was taken with,
+    so a capture of other kernels is reported as stale instead of being quoted."""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "rti_b200", "csrc")
-    for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh")) or name in ("ptm_kernels.h", "ptm_internal.h"):
-            h.update(name.encode())
-            h.update(open(os.path.join(d, name), "rb").read())
+    for name in ("ptm_fit_tma.cu", "ptm_quantise.cu", "ptm_device.cuh", "ptm_tma.cuh", "ptm_kernels.h", "ptm_internal.h"):
+        h.update(name.encode())
+        h.update(open(os.path.join(d, name), "rb").read())
     return h.hexdigest()
 
 
