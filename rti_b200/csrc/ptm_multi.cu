@@ -433,8 +433,11 @@ int ptmb_multi_encode_host(ptmb_multi_t *m, const void *stack_host, int sample_t
     // equal slabs); results do not depend on the split (tests/test_gpu_multi.py)
     if (!m->calibrated && image_bytes * n_lights >= ((size_t) 256 << 20)) {
         const char *env = getenv("PTM_MULTI_BALANCE");
-        if (!(env && env[0] == '0') && ptmb_multi_calibrate_h2d(m, 0.012, nullptr))
-            return 1;
+        if (!(env && env[0] == '0') && ptmb_multi_calibrate_h2d(m, 0.012, nullptr)) {
+            // the probe is an optimisation: without it (no pinned memory to be had, ...) the slabs stay equal
+            cudaGetLastError();
+            m->weight.assign(m->n, 1.0);
+        }
         m->calibrated = true;
     }
     std::vector<ptmb_scale_bias_t> sb(m->n);
