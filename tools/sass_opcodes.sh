@@ -4,6 +4,7 @@
 # The mnemonics are the ones /opt/skills/guides/B200_PROFILING.md names as proof of Blackwell-native code:
 #   UTCIMMA / UTCHMMA  tcgen05.mma     LDTM      tcgen05.ld (TMEM -> registers)     UTCBAR   tcgen05.commit
 #   UTMALDG / UTMASTG  TMA tensor copy UBLKCP    cp.async.bulk (1-D bulk copy)      SYNCS    mbarrier
+#   HMMA              mma.sync (legacy register-fragment MMA: the RGB relight kernel)
 #   FFMA2 / FMUL2      packed f32x2    I2IP      cvt.pack.sat (saturating byte pack) VIMNMX   packed integer min/max
 LIB=${1:-rti_b200/lib/libptm_b200.so}
 echo "# $LIB  ($(git log -1 --format=%h 2>/dev/null))"
@@ -20,7 +21,7 @@ cuobjdump -sass "$LIB" | awk '
 /Function :/ { fn=$3; next }
 /^[[:space:]]+\/\*[0-9a-f]{4}\*\// {
     op=$2; sub(/;$/,"",op); split(op, parts, "."); base=parts[1];
-    if (base ~ /^(UTCIMMA|UTCHMMA|UTCQMMA|LDTM|STTM|UTCBAR|UTMALDG|UTMASTG|UBLKCP|SYNCS|FFMA2|FMUL2|FADD2|I2IP|VIMNMX|FFMA|ACQBULK|REDUX)$/)
+    if (base ~ /^(HMMA|UTCIMMA|UTCHMMA|UTCQMMA|LDTM|STTM|UTCBAR|UTMALDG|UTMASTG|UBLKCP|SYNCS|FFMA2|FMUL2|FADD2|I2IP|VIMNMX|FFMA|ACQBULK|REDUX)$/)
         n[fn, base]++
     total[fn]++
 }
