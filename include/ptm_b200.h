@@ -287,8 +287,9 @@ int ptmb_encode_lrgb_dev (ptmb_ctx_t *ctx, ptmb_xchg_t *xchg, const void *stack_
  *   ptmb_multi_encode_host     ptmb_encode_host across the GPUs: ONE host stack / ONE set of host blocks
  *                              in the caller's layout; each GPU streams its rows (synchronous).  The rows are
  *                              split in proportion to the host bandwidth each GPU gets when all copy at once
- *                              (measured once, by the first call with a stack of 256 MB or more; equal slabs
- *                              with PTM_MULTI_BALANCE=0) -- the result does not depend on the split
+ *                              (measured once, by the first call with a stack of 256 MB or more, and corrected
+ *                              from the copy times of later encodes; equal slabs with PTM_MULTI_BALANCE=0) --
+ *                              the result does not depend on the split
  *   ptmb_multi_host_slab       the rows GPU i takes in ptmb_multi_encode_host for an image of `height` rows
  *   ptmb_multi_set_host_weights  explicit shares (n_dev positive numbers; NULL = equal)
  *   ptmb_multi_calibrate_h2d   measure the shares now: every GPU copies pinned host memory for `seconds`

@@ -14,7 +14,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -66,6 +68,8 @@ struct ptmb_multi {
     bool calibrated = false;
     bool explicit_weights = false;   // set by ptmb_multi_set_host_weights: never adjusted automatically
     int refinements = 0;             // automatic adjustments made from the copy times of real encodes
+    int host_encodes = 0;            // large host encodes since the last calibration (the first one also pays for
+                                     // allocations and first launches: its copy times are not used)
 
     // rows [cut(i), cut(i+1)) belong to GPU i
     size_t cut(size_t height, int i) const {
@@ -388,6 +392,7 @@ int ptmb_multi_calibrate_h2d(ptmb_multi_t *m, double seconds, double *gbs_out) {
     m->calibrated = true;
     m->explicit_weights = false;
     m->refinements = 0;
+    m->host_encodes = 0;
     return 0;
 }
 
@@ -474,8 +479,18 @@ int ptmb_multi_encode_host(ptmb_multi_t *m, const void *stack_host, int sample_t
         return rc;
     // The probe's small copies do not load the links exactly like slab-sized ones: while the split was chosen
     // automatically, the copy times of this encode (first to last input byte per GPU) correct it for the next
-    // one -- rows follow rows_i / t_i when the GPUs finished more than 4 % apart (at most 3 corrections).
-    if (m->calibrated && !m->explicit_weights && m->refinements < 3 && image_bytes * n_lights >= ((size_t) 256 << 20)) {
+    // one when the GPUs finished more than 6 % apart (at most 3 corrections, never from the first encode).
+    const bool large = image_bytes * n_lights >= ((size_t) 256 << 20);
+    if (large)
+        ++m->host_encodes;
+    static const bool debug = getenv("PTM_MULTI_DEBUG") != nullptr;
+    if (debug) {
+        fprintf(stderr, "ptmb_multi_encode_host #%d: rows / copy ms per GPU:", m->host_encodes);
+        for (int i = 0; i < m->n; ++i)
+            fprintf(stderr, " %zu/%.2f", m->cut(height, i + 1) - m->cut(height, i), copy_ms[i]);
+        fprintf(stderr, "  (refinements so far %d)\n", m->refinements);
+    }
+    if (m->calibrated && !m->explicit_weights && m->refinements < 3 && large && m->host_encodes >= 2) {
         const std::vector<double> &ms = copy_ms;
         double lo = 1e300, hi = 0;
         bool ok = true;
@@ -485,10 +500,17 @@ int ptmb_multi_encode_host(ptmb_multi_t *m, const void *stack_host, int sample_t
             lo = std::min(lo, ms[i]);
             hi = std::max(hi, ms[i]);
         }
-        if (ok && hi > 1.04 * lo) {
-            std::vector<double> w(m->n);
+        if (ok && hi > 1.06 * lo) {
+            // damped (half the indicated correction, each share changed by at most 25 %): the copy times carry a few
+            // per cent of noise, and the links are coupled -- what one GPU gives up the others do not simply gain
+            double mean = 0;
             for (int i = 0; i < m->n; ++i)
-                w[i] = (double) (m->cut(height, i + 1) - m->cut(height, i)) / ms[i];
+                mean += ms[i] / m->n;
+            std::vector<double> w(m->n);
+            for (int i = 0; i < m->n; ++i) {
+                const double corr = std::min(1.25, std::max(0.8, std::sqrt(mean / ms[i])));
+                w[i] = (double) (m->cut(height, i + 1) - m->cut(height, i)) * corr;
+            }
             m->weight = w;
             ++m->refinements;
         }
