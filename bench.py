@@ -451,7 +451,7 @@ def run_extras(M60, L60, peak, gpu_index):
     bpp = N_LIGHTS * 3 + 9
     for engine in ("ffma", "mma"):
         time.sleep(3.0)
-        e2 = PtmEncoder(W, H, M60, planes=1, engine=engine)
+        e2 = PtmEncoder(W, H, M60, planes=1, engine=engine, keep_coeffs=os.environ.get("PTM_KEEP_COEFFS", "0") == "1")
         record("headline 24MP x 60 LRGB u8, 500 fits back to back (sustained clocks), %s engine" % engine,
                lambda: e2.encode(stack), 500, P, P * bpp, "Mpixel/s", algorithmic_bytes_per_px=bpp,
                l2="stack larger than L2, streamed once per step")
@@ -562,8 +562,11 @@ def run_b200(args):
     P = rows * W
 
     stack = torch.empty((N_LIGHTS, rows, W, 3), dtype=torch.uint8, device="cuda")
-    enc = PtmEncoder(W, rows, M, planes=1, keep_coeffs=os.environ.get("PTM_KEEP_COEFFS", "1") == "1",
-                     exchange=os.environ.get("PTM_EXCHANGE", "p2p"))
+    # the float coefficients are an intermediate of the encode (the reference's encoder frees them after
+    # ptm_scale_coefficients): declared scratch, K2 may drop their L2 lines instead of sending them to HBM and back
+    # (ptmb_set_coeffs_scratch; PTM_KEEP_COEFFS=1 measures with the float plane kept as an output)
+    keep_coeffs = os.environ.get("PTM_KEEP_COEFFS", "0") == "1"
+    enc = PtmEncoder(W, rows, M, planes=1, keep_coeffs=keep_coeffs, exchange=os.environ.get("PTM_EXCHANGE", "p2p"))
     enc.ctx.synth(SEED, 0, U8, r0 * W, P, light_q14(L), stack, P * 3)
     torch.cuda.synchronize()
     # the stack is resident and complete before the first encode is enqueued: K1's copy warp may start while the
@@ -761,6 +764,9 @@ def run_b200(args):
                                                % (stack.numel() / 1e6),
                    "driver": "one process per GPU (torchrun)" if world > 1 else "one process",
                    "stack_stable": stack_stable,
+                   "float_plane": "kept as an output" if keep_coeffs else
+                                  "scratch (ptmb_set_coeffs_scratch): K2 quantises its L2-resident end first and "
+                                  "discards those lines; parity of the floats is checked on a separate encode that keeps them",
                    "timed_region": "K back-to-back encodes between two CUDA events, nothing else enqueued" +
                                    ("; one untimed encode after the barrier lines the ranks up on the device first"
                                     if world > 1 else ""),
@@ -792,6 +798,16 @@ def run_b200(args):
             from oracle import oracle as O  # noqa: F401  (cpu_baseline leg: the one place bench may run the oracle)
             stack_np = host_stack.numpy() if host_stack is not None else stack.cpu().numpy()
             out["cpu_baseline"], ref = cpu_baseline(stack_np, L, M, args.cpu_seconds)
+            if not keep_coeffs:
+                # the timed encodes left the float plane undefined: their bytes must equal those of an encode that
+                # keeps it, and that encode's floats are the ones compared with the reference
+                timed_bytes, timed_rgb, timed_sb = enc.coef_bytes.clone(), enc.rgb.clone(), enc.sb.clone()
+                enc.ctx.set_coeffs_scratch(False)
+                enc.encode(stack)
+                torch.cuda.synchronize()
+                assert torch.equal(timed_bytes, enc.coef_bytes) and torch.equal(timed_rgb, enc.rgb) and \
+                    torch.equal(timed_sb, enc.sb), "scratch-plane encode differs from the encode that keeps its floats"
+                del timed_bytes, timed_rgb, timed_sb
             out["parity"] = parity_vs_reference(enc, ref, M, stack_np)
             if not args.no_dropin:
                 out["e2e_dropin"] = run_dropin(stack_np, L, (enc.coef_bytes[0].cpu().numpy(), enc.rgb.cpu().numpy()))

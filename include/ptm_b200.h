@@ -333,6 +333,15 @@ int ptmb_encode_rgb_dev (ptmb_ctx_t *ctx, ptmb_xchg_t *xchg, const void *stack_d
  * an 8-GPU slab takes 0.12 ms).  Default 0: K1 waits for the previous kernel before it reads anything. */
 int ptmb_set_stack_stable (ptmb_ctx_t *ctx, int stable);
 
+/* The float coefficients are an INTERMEDIATE of a whole encode (the reference's encoder allocates them, hands them
+ * to ptm_scale_coefficients and frees them, rti-builder/ptm-encoder.c:313,406,409).  scratch != 0 declares the
+ * coeffs_dev plane of ptmb_encode_lrgb_dev / ptmb_encode_rgb_dev scratch: its contents are undefined after the call.
+ * K2 then quantises the end of the plane first -- the part K1 wrote last, still dirty in L2 -- and discards every L2
+ * line it has read, so those lines are neither fetched from nor written back to HBM (24 MP: 80 MB less traffic and
+ * 1 % per encode; a 3 MP slab, whose plane fits L2: 4 %).  The bytes, the colour block and scale / bias are the
+ * same either way.  Default 0: the float plane is an output. */
+int ptmb_set_coeffs_scratch (ptmb_ctx_t *ctx, int scratch);
+
 /* Timing probes for benchmarks: the next `pairs` ptmb_encode_lrgb_dev calls bracket their fit
  * stage with CUDA events on the context's stream; _read synchronises and returns milliseconds. */
 int ptmb_probe_arm (ptmb_ctx_t *ctx, unsigned pairs);

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "ptmb_keys_init": ([_vp, _vp], _int),
     "ptmb_fit_lrgb": ([_vp, _vp, _int, _sz, _sz, _vp, _vp, _vp], _int),
     "ptmb_set_stack_stable": ([_vp, _int], _int),
+    "ptmb_set_coeffs_scratch": ([_vp, _int], _int),
     "ptmb_set_fit_mode": ([_vp, _int], _int),
     "ptmb_fit_rgb": ([_vp, _vp, _int, _sz, _sz, _vp, _sz, _vp], _int),
     "ptmb_fit_channel": ([_vp, _vp, _int, _sz, _sz, _sz, _vp], _int),

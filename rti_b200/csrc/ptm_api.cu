@@ -307,6 +307,12 @@ int ptmb_fit_lrgb(ptmb_ctx_t *c, const void *stack_dev, int sample_type, size_t 
     return 0;
 }
 
+int ptmb_set_coeffs_scratch(ptmb_ctx_t *c, int scratch) {
+    REQUIRE(c, "ctx is NULL");
+    c->coeffs_scratch = scratch != 0;
+    return 0;
+}
+
 int ptmb_set_stack_stable(ptmb_ctx_t *c, int stable) {
     REQUIRE(c, "ctx is NULL");
     c->stack_stable = stable != 0;
@@ -461,7 +467,9 @@ int ptmb_encode_lrgb_dev(ptmb_ctx_t *c, ptmb_xchg_t *x, const void *stack_dev, i
     }
     if (ev1)
         CK(cudaEventRecord(ev1, c->stream));
-    CK(ptm::launch_quantise(coeffs_dev, pixels, src, coef_bytes_dev, sb_dev, false, c->sm_count, c->stream));
+    // scratch plane (ptmb_set_coeffs_scratch): K2 takes the L2-resident end of the plane first and discards its lines
+    CK(ptm::launch_quantise(coeffs_dev, pixels, src, coef_bytes_dev, sb_dev, c->coeffs_scratch != 0, c->sm_count,
+                            c->stream));
     if (!src.mailbox)
         CK(ptm::launch_keys_init(c->keys_dev, c->stream));   // leave the context keys reset, as the hand-off does
     return 0;
@@ -516,7 +524,8 @@ int ptmb_encode_rgb_dev(ptmb_ctx_t *c, ptmb_xchg_t *x, const void *stack_dev, in
             return 1;
         src.keys = c->keys_dev;
     }
-    CK(ptm::launch_quantise(coeffs_dev, pixels * 3, src, coef_bytes_dev, sb_dev, false, c->sm_count, c->stream));
+    CK(ptm::launch_quantise(coeffs_dev, pixels * 3, src, coef_bytes_dev, sb_dev, c->coeffs_scratch != 0, c->sm_count,
+                            c->stream));
     if (!src.mailbox)
         CK(ptm::launch_keys_init(c->keys_dev, c->stream));
     return 0;

@@ -58,6 +58,7 @@ struct ptmb_ctx {
     int relight_mode = 0;                    // PTMB_RELIGHT_*
     int fit_mode = 0;                        // PTMB_FIT_* flags of the LRGB-shaped entries
     int stack_stable = 0;                    // ptmb_set_stack_stable
+    int coeffs_scratch = 0;                  // ptmb_set_coeffs_scratch
     int *keys_dev = nullptr;                 // scratch for the host-buffer entry points
     ptmb_scale_bias_t *sb_dev = nullptr;
     std::vector<float> light_host;

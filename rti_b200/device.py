@@ -91,6 +91,11 @@ class Context:
         code = {"default": 0, "ffma": 1, "mma": 2}[engine] if isinstance(engine, str) else int(engine)
         _lib.check(self._lib.ptmb_set_fit_engine(self._h, code))
 
+    def set_coeffs_scratch(self, scratch=True):
+        """Declare the float plane of the fused encodes scratch (undefined afterwards): K2 quantises its L2-resident
+        end first and discards the lines, so they never travel to HBM and back."""
+        _lib.check(self._lib.ptmb_set_coeffs_scratch(self._h, 1 if scratch else 0))
+
     def set_stack_stable(self, stable=True):
         """Promise that stacks passed to encode_lrgb_dev are not written by earlier work on the stream (lets K1's
         copy warp start before the previous kernel has drained)."""

@@ -95,6 +95,7 @@ class PtmEncoder:
         self.keys = torch.empty(NKEYS, dtype=torch.int32, device=dev)
         self.sb = torch.empty(NKEYS, dtype=torch.int32, device=dev)  # 6 floats + 6 ints, raw
         self.keep_coeffs = bool(keep_coeffs)
+        self.ctx.set_coeffs_scratch(not self.keep_coeffs)   # keep_coeffs=False: self.coeffs is scratch after encode()
         self.xchg = make_key_exchange(self.ctx, group) if exchange == "p2p" and not single else None
         import torch.distributed as dist
         multi = not single and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
@@ -149,7 +150,7 @@ class PtmEncoder:
             self.ctx.encode_lrgb_dev(stack, self.pixels * 3 * stack.element_size(), self.pixels, self.coeffs,
                                      self.rgb, self.coef_bytes, self.sb, xchg=self.xchg, sample_type=st)
             return
-        if self.planes == 3 and self.exchange_kind in ("none", "p2p") and self.keep_coeffs and stack.is_contiguous():
+        if self.planes == 3 and self.exchange_kind in ("none", "p2p") and stack.is_contiguous():
             # RGB formats: tensor-core K1 with the key hand-off + one K2 over the three planes (two launches)
             self._use_current_stream()
             st = {torch.uint8: U8, torch.uint16: U16}[stack.dtype]

@@ -174,6 +174,8 @@ def bench_multi(args, B):
         slabs.append((r0, r1))
         mg.ctx[i].synth(B.SEED, 0, U8, r0 * W, P, light_q14(L), stacks[i], P * 3)
     mg.synchronize()
+    for c in mg.ctx:   # the float planes are scratch here too (see bench.py): K2 may drop their L2 lines
+        c.set_coeffs_scratch(os.environ.get("PTM_KEEP_COEFFS", "0") != "1")
     a = mg.make_dev_args(stacks, coeffs, rgbs, cbytes, sbs)
     for _ in range(max(args.warmup, 3)):
         mg.encode_lrgb_dev(a)

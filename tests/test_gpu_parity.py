@@ -150,6 +150,36 @@ def test_lrgb_ring_tile_sizes_give_the_same_bytes(ctx, oracle, dome1, M60, W, H,
         np.testing.assert_array_equal(res["512"][k], res["1024"][k])
 
 
+@pytest.mark.parametrize("planes", [1, 3])
+def test_scratch_float_plane_gives_the_same_blocks(oracle, dome1, M60, planes, monkeypatch):
+    """ptmb_set_coeffs_scratch: K2 quantises the end of the float plane first and discards the L2 lines it has read
+    (the plane is undefined afterwards).  Bytes, colour block and scale / bias must equal those of an encode that keeps
+    its floats -- for a plane that is all tail, and (PTM_K2_TAIL_MB=1) for planes split into a 1 MB tail and a head,
+    with pixel counts that are and are not multiples of 16 (the latter take the plain forward kernel)."""
+    from rti_b200.device import U8, light_q14
+    from rti_b200.encoder import PtmEncoder
+    for W, H in ((2000, 752), (1040, 37), (1000, 333)):
+        P = W * H
+        stack = torch.empty((60, H, W, 3), dtype=torch.uint8, device="cuda")
+        keep = PtmEncoder(W, H, M60, planes=planes, keep_coeffs=True)
+        keep.ctx.synth(0x5EED0010 + W, 0 if planes == 1 else 1, U8, 0, P, light_q14(dome1), stack, P * 3)
+        keep.encode(stack)
+        torch.cuda.synchronize()
+        for tail in (None, "1"):
+            if tail:
+                monkeypatch.setenv("PTM_K2_TAIL_MB", tail)
+            scratch = PtmEncoder(W, H, M60, planes=planes, keep_coeffs=False)
+            for _ in range(3):
+                scratch.encode(stack)
+            torch.cuda.synchronize()
+            assert torch.equal(scratch.coef_bytes, keep.coef_bytes), (W, H, tail)
+            assert torch.equal(scratch.sb, keep.sb)
+            if planes == 1:
+                assert torch.equal(scratch.rgb, keep.rgb)
+            if tail:
+                monkeypatch.delenv("PTM_K2_TAIL_MB")
+
+
 @pytest.mark.parametrize("engine", ["ffma", "mma"])
 def test_plain_and_fused_entry_points_interleave(ctx, oracle, dome1, M60, engine):
     """The dynamic tile schedule keeps a device counter at 0 between launches; the plain fit (cleared by a
