@@ -382,6 +382,7 @@ def run_extras(M60, L60, peak, gpu_index):
     from rti_b200.encoder import PtmEncoder, PtmRelighter
     from rti_b200.ptmlib import ptm_svd
     out = []
+    keep = os.environ.get("PTM_KEEP_COEFFS", "0") == "1"
 
     def record(name, fn, reps, units, alg_bytes, unit_name, **more):
         s = ClockSampler(gpu_index)
@@ -398,7 +399,7 @@ def run_extras(M60, L60, peak, gpu_index):
         n, P = len(L), W * H
         M = ptm_svd(L)
         stack = torch.empty((n, H, W, 3), dtype=td, device="cuda")
-        enc = PtmEncoder(W, H, M, planes=planes)
+        enc = PtmEncoder(W, H, M, planes=planes, keep_coeffs=keep)     # float plane as in the headline run
         enc.ctx.synth(SEED, mode, st, 0, P, light_q14(L), stack, P * 3 * stack.element_size())
         bpp = n * 3 * stack.element_size() + (18 if planes == 3 else 9)
         record(name, lambda: enc.encode(stack), reps, P, P * bpp, "Mpixel/s", algorithmic_bytes_per_px=bpp,
@@ -451,7 +452,7 @@ def run_extras(M60, L60, peak, gpu_index):
     bpp = N_LIGHTS * 3 + 9
     for engine in ("ffma", "mma"):
         time.sleep(3.0)
-        e2 = PtmEncoder(W, H, M60, planes=1, engine=engine, keep_coeffs=os.environ.get("PTM_KEEP_COEFFS", "0") == "1")
+        e2 = PtmEncoder(W, H, M60, planes=1, engine=engine, keep_coeffs=keep)
         record("headline 24MP x 60 LRGB u8, 500 fits back to back (sustained clocks), %s engine" % engine,
                lambda: e2.encode(stack), 500, P, P * bpp, "Mpixel/s", algorithmic_bytes_per_px=bpp,
                l2="stack larger than L2, streamed once per step")
