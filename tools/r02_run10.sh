@@ -1,5 +1,6 @@
 #!/bin/bash
 # round 2, GPU call 10: tensor-core RGB relight kernel (parity, chunk shapes, FFMA kernel beside it, ncu capture)
+# NOTE: the PTM_RELIGHT_MMA_SHAPE numbers of this run are those of the tuning build (legend in profiles/r02_relight_rgb_mma.txt)
 O=gpurun_out
 mkdir -p $O
 timeout 900 python -m pytest tests/test_gpu_relight_fast.py -m gpu -x -q -s > $O/r02j_pytest.log 2>&1; echo "pytest rc=$?" >> $O/r02j_pytest.log

@@ -1,5 +1,6 @@
 #!/bin/bash
 # round 2, GPU call 11: tensor-core RGB relight kernel shapes (timing only), then ncu of the chosen one
+# NOTE: the PTM_RELIGHT_MMA_SHAPE numbers of this run are those of the tuning build (legend in profiles/r02_relight_rgb_mma.txt)
 O=gpurun_out
 mkdir -p $O
 {

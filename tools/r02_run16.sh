@@ -1,5 +1,7 @@
 #!/bin/bash
 # round 2, GPU call 16: K2 walking the float plane backwards with L2 discards inside the FUSED encode (PTM_K2_CONSUME=1):
+# NOTE: PTM_K2_CONSUME (whole plane backwards) existed only in the intermediate build this script ran against; the shipped form is
+# ptmb_set_coeffs_scratch (tail first, bench.py default; PTM_KEEP_COEFFS=1 keeps the float plane) -- see tools/r02_run17.sh
 # HBM traffic of whole encodes (range replay) and step time, 24 MP and 6 MP
 O=gpurun_out
 mkdir -p $O

@@ -1,5 +1,6 @@
 #!/bin/bash
 # round 2, GPU call 17: tail-first consuming K2 inside the fused encode: parity test, HBM traffic (range replay), step time
+# NOTE: run17 drove the scratch plane with PTM_K2_CONSUME=0|1 of the intermediate build; today: PTM_KEEP_COEFFS=1|0
 O=gpurun_out
 mkdir -p $O
 M=dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum
