@@ -106,6 +106,10 @@ def read_traffic(kernels):
         per = {k: float(t[k]["dram_bytes_read"]) + float(t[k]["dram_bytes_write"]) for k in kernels}
     except Exception:
         return None, "profiles/traffic.json lacks " + ", ".join(kernels)
+    whole = t.get("whole_encode_range_replay")
+    if whole:   # HBM bytes of a WHOLE encode with L2 left alone between K1 and K2 (ncu range replay), both plane modes
+        per["_whole_encode"] = {k: float(v["dram_bytes_read"]) + float(v["dram_bytes_write"])
+                                for k, v in whole.items() if isinstance(v, dict)}
     return per, t.get("source", "profiles/traffic.json")
 
 
@@ -752,9 +756,10 @@ def run_b200(args):
     peak, peak_src = measured_peak()
     k1_gbs = ALG_BYTES_K1 * P / (k1_ms * 1e-3) / 1e9
     path_gbs = ALG_BYTES_PATH * W * H / (ms_step * 1e-3) / 1e9 / world
-    traffic, traffic_src = (None, "single-GPU captures only")
+    traffic, traffic_src, whole_encode = None, "single-GPU captures only", None
     if world == 1 and (W, H) == (WIDTH, HEIGHT):
         per, traffic_src = read_traffic(["fit_lrgb_u8_tma_kernel", "quantise_kernel"])
+        whole_encode = per.pop("_whole_encode", None) if per else None
         traffic = None if per is None else sum(per.values())
     out = {
         "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
@@ -779,6 +784,7 @@ def run_b200(args):
                      "algorithmic_bytes_per_px": ALG_BYTES_PATH, "peak_source": peak_src,
                      "traffic": traffic, "traffic_ratio": None if traffic is None else traffic / (ALG_BYTES_PATH * W * H),
                      "traffic_source": traffic_src,
+                     "traffic_whole_encode_range_replay": whole_encode,
                      "k1_ms": k1_ms, "k1_timed_in": "a second pass of the same loop with CUDA events around K1 "
                                                      "(%.4f ms per step there)" % probed_ms,
                      "k1_achieved": k1_gbs, "k1_frac": k1_gbs / peak,
