@@ -289,6 +289,16 @@ def parity_vs_reference(enc, ref, M, stack_np):
     return out
 
 
+def golden_blocks_sha256(W, H):
+    """The committed hash of the single-GPU blocks of the default workload (tests/golden), or None."""
+    if (W, H) != (WIDTH, HEIGHT):
+        return None
+    try:
+        return json.load(open(os.path.join(ROOT, "tests", "golden", "blocks_24mp_lrgb_sha256.json")))["sha256"]
+    except Exception:
+        return None
+
+
 def sharded_identity(enc, M, L, W, H, r0, r1, world):
     """This rank's sharded blocks against ITS OWN single-GPU encode of the whole image: byte-identical or not."""
     import torch
@@ -653,7 +663,9 @@ def run_b200(args):
     sharded, single_blocks = None, None
     if world > 1:
         same, digest, single_blocks = sharded_identity(enc, M, L, W, H, r0, r1, world)
+        gold = golden_blocks_sha256(W, H)
         sharded = {"sharded_identical": same, "single_gpu_blocks_sha256": digest,
+                   "matches_golden_sha256": None if gold is None else bool(gold == digest),
                    "how": "every rank encodes the whole image on its own GPU (no exchange) and compares its slab"}
 
     # ---- end to end through the host-buffer C-ABI call.  The rows are split over the ranks in proportion to the
@@ -816,6 +828,10 @@ def run_b200(args):
                     torch.equal(timed_sb, enc.sb), "scratch-plane encode differs from the encode that keeps its floats"
                 del timed_bytes, timed_rgb, timed_sb
             out["parity"] = parity_vs_reference(enc, ref, M, stack_np)
+            digest = hashlib.sha256(enc.coef_bytes[0].cpu().numpy().tobytes() + enc.rgb.cpu().numpy().tobytes()).hexdigest()
+            gold = golden_blocks_sha256(W, H)
+            out["parity"]["blocks_sha256"] = digest
+            out["parity"]["matches_golden_sha256"] = None if gold is None else bool(gold == digest)
             if not args.no_dropin:
                 out["e2e_dropin"] = run_dropin(stack_np, L, (enc.coef_bytes[0].cpu().numpy(), enc.rgb.cpu().numpy()))
     print(json.dumps(out))

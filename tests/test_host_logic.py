@@ -115,3 +115,11 @@ def test_weighted_row_cuts_cover_the_image():
                 for i in range(n):
                     assert abs((cuts[i + 1] - cuts[i]) - H * w[i] / tot) <= 1.0
     assert bench.weighted_cuts(4000, [23.3] * 4 + [35.3] * 4) == [0, 398, 795, 1193, 1590, 2193, 2795, 3398, 4000]
+
+
+def test_golden_block_hash_is_wired_into_the_bench():
+    """bench.py compares the single-GPU blocks of its default workload with a committed SHA-256 (N = 1 and N > 1 lines)."""
+    import bench
+    h = bench.golden_blocks_sha256(bench.WIDTH, bench.HEIGHT)
+    assert isinstance(h, str) and len(h) == 64 and int(h, 16) >= 0
+    assert bench.golden_blocks_sha256(64, 48) is None
